@@ -1,0 +1,245 @@
+"""Minimal heterogeneous-graph containers with the torch_geometric surface the hot path touches.
+
+The reference feeds `sampling()` / `model(data)` PyG `HeteroData` / `Batch` objects
+(utils/sampling.py:78,89-91; datasets/process_mols.py:567-589,448-527).  PyG is not a
+dependency of this package: these containers accept the same attribute / key syntax
+(`data['ligand'].pos`, `data['ligand', 'ligand'].edge_index`, `data.num_graphs`,
+`Batch.from_data_list`, `to_data_list`, `.to(device)`), and every consumer in this
+package is duck-typed, so real PyG objects work as well.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any, Dict, List
+
+import numpy as np
+import torch
+
+
+class _Store:
+    """Attribute bag for one node type or one edge type."""
+
+    def __init__(self, key):
+        object.__setattr__(self, "_key", key)
+        object.__setattr__(self, "_d", {})
+
+    def __getattr__(self, name):
+        d = object.__getattribute__(self, "_d")
+        if name in d:
+            return d[name]
+        if name == "num_nodes":
+            for k in ("x", "pos", "batch"):
+                if k in d and torch.is_tensor(d[k]):
+                    return d[k].shape[0]
+            raise AttributeError(name)
+        if name == "num_edges":
+            if "edge_index" in d:
+                return d["edge_index"].shape[1]
+            raise AttributeError(name)
+        raise AttributeError(f"{object.__getattribute__(self, '_key')!r} store has no attribute {name!r}")
+
+    def __setattr__(self, name, value):
+        self._d[name] = value
+
+    def __delattr__(self, name):
+        del self._d[name]
+
+    def __contains__(self, name):
+        return name in self._d
+
+    def keys(self):
+        return self._d.keys()
+
+    def items(self):
+        return self._d.items()
+
+    def is_edge(self):
+        return isinstance(self._key, tuple)
+
+
+class HeteroData:
+    def __init__(self):
+        object.__setattr__(self, "_stores", {})
+        object.__setattr__(self, "_g", {})
+
+    # -- stores ---------------------------------------------------------------
+    def _resolve(self, key):
+        if isinstance(key, tuple) and len(key) == 2:
+            hits = [k for k in self._stores if isinstance(k, tuple) and k[0] == key[0] and k[2] == key[1]]
+            if len(hits) == 1:
+                return hits[0]
+            if not hits:
+                return (key[0], "to", key[1])
+            raise KeyError(f"ambiguous edge type {key}")
+        return key
+
+    def __getitem__(self, key):
+        key = self._resolve(key)
+        if key not in self._stores:
+            self._stores[key] = _Store(key)
+        return self._stores[key]
+
+    @property
+    def node_types(self):
+        return [k for k in self._stores if not isinstance(k, tuple)]
+
+    @property
+    def edge_types(self):
+        return [k for k in self._stores if isinstance(k, tuple)]
+
+    # -- graph-level attributes ----------------------------------------------
+    def __getattr__(self, name):
+        g = object.__getattribute__(self, "_g")
+        if name in g:
+            return g[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self._g[name] = value
+
+    def __contains__(self, name):
+        return name in self._g
+
+    @property
+    def num_graphs(self):
+        return self._g.get("_num_graphs", 1)
+
+    # -- movement -------------------------------------------------------------
+    def _apply(self, fn):
+        def mv(v):
+            if torch.is_tensor(v):
+                return fn(v)
+            if isinstance(v, dict):
+                return {k: mv(u) for k, u in v.items()}
+            return v
+        for st in self._stores.values():
+            for k in list(st.keys()):
+                st._d[k] = mv(st._d[k])
+        for k in list(self._g.keys()):
+            if not k.startswith("_"):
+                self._g[k] = mv(self._g[k])
+        return self
+
+    def to(self, device, non_blocking=False):
+        return self._apply(lambda t: t.to(device, non_blocking=non_blocking))
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+
+def _is_cat_tensor(v):
+    return torch.is_tensor(v) and v.dim() >= 1
+
+
+class Batch(HeteroData):
+    @classmethod
+    def from_data_list(cls, data_list: List[HeteroData]):
+        b = cls()
+        n = len(data_list)
+        first = data_list[0]
+        counts: Dict[Any, List[int]] = {}
+        for nt in first.node_types:
+            counts[nt] = [d[nt].num_nodes for d in data_list]
+        offs = {nt: np.concatenate([[0], np.cumsum(c)]) for nt, c in counts.items()}
+        slices: Dict[Any, Dict[str, List[int]]] = {}
+        for nt in first.node_types:
+            st = b[nt]
+            slices[nt] = {}
+            for k in first[nt].keys():
+                vals = [d[nt]._d[k] for d in data_list]
+                if _is_cat_tensor(vals[0]):
+                    st._d[k] = torch.cat(vals, 0)
+                    slices[nt][k] = [0] + list(np.cumsum([v.shape[0] for v in vals]))
+                else:
+                    st._d[k] = vals
+            dev = next((v.device for v in st._d.values() if torch.is_tensor(v)), torch.device("cpu"))
+            st._d["batch"] = torch.repeat_interleave(torch.arange(n, device=dev),
+                                                     torch.tensor(counts[nt], device=dev))
+            st._d["ptr"] = torch.tensor(offs[nt], dtype=torch.long, device=dev)
+        for et in first.edge_types:
+            st = b[et]
+            slices[et] = {}
+            for k in first[et].keys():
+                vals = [d[et]._d[k] for d in data_list]
+                if k == "edge_index":
+                    sh = [torch.tensor([[offs[et[0]][i]], [offs[et[2]][i]]], dtype=v.dtype, device=v.device)
+                          for i, v in enumerate(vals)]
+                    st._d[k] = torch.cat([v + s for v, s in zip(vals, sh)], 1)
+                    slices[et][k] = [0] + list(np.cumsum([v.shape[1] for v in vals]))
+                elif _is_cat_tensor(vals[0]):
+                    st._d[k] = torch.cat(vals, 0)
+                    slices[et][k] = [0] + list(np.cumsum([v.shape[0] for v in vals]))
+                else:
+                    st._d[k] = vals
+        for k in first._g.keys():
+            if k.startswith("_"):
+                continue
+            vals = [d._g[k] for d in data_list]
+            if _is_cat_tensor(vals[0]):
+                b._g[k] = torch.cat(vals, 0)
+            elif torch.is_tensor(vals[0]):
+                b._g[k] = torch.stack(vals, 0)
+            else:
+                b._g[k] = vals
+        b._g["_num_graphs"] = n
+        b._g["_slices"] = slices
+        b._g["_offs"] = offs
+        return b
+
+    def to_data_list(self) -> List[HeteroData]:
+        n, slices, offs = self.num_graphs, self._g["_slices"], self._g["_offs"]
+        out = []
+        for i in range(n):
+            d = HeteroData()
+            for key, st in self._stores.items():
+                for k, v in st.items():
+                    if k in ("batch", "ptr"):
+                        continue
+                    sl = slices.get(key, {}).get(k)
+                    if sl is not None and torch.is_tensor(v):
+                        if k == "edge_index":
+                            sh = torch.tensor([[offs[key[0]][i]], [offs[key[2]][i]]], dtype=v.dtype, device=v.device)
+                            d[key]._d[k] = v[:, sl[i]: sl[i + 1]] - sh
+                        else:
+                            d[key]._d[k] = v[sl[i]: sl[i + 1]]
+                    elif isinstance(v, list) and len(v) == n:
+                        d[key]._d[k] = v[i]
+                    # per-step tensors added after collation (node_t, sigma embeddings...) are dropped
+            for k, v in self._g.items():
+                if k.startswith("_"):
+                    continue
+                if torch.is_tensor(v) and v.shape[:1] == (n,):
+                    d._g[k] = v[i: i + 1]
+                elif isinstance(v, list) and len(v) == n:
+                    d._g[k] = v[i]
+            out.append(d)
+        return out
+
+
+class DataLoader:
+    """Sequential, non-shuffling stand-in for torch_geometric.loader.DataLoader (sampling.py:78)."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, **kw):
+        assert not shuffle
+        self.dataset, self.batch_size = dataset, batch_size
+
+    def __len__(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for i in range(0, len(self.dataset), self.batch_size):
+            yield Batch.from_data_list([self.dataset[j] for j in range(i, min(i + self.batch_size, len(self.dataset)))])
+
+
+def subgraph(subset, edge_index, edge_attr=None, relabel_nodes=False, num_nodes=None):
+    """Keep edges with both ends in `subset` (bool mask); optionally renumber (utils/utils.py:411-412)."""
+    mask = subset if subset.dtype == torch.bool else torch.zeros(num_nodes, dtype=torch.bool).index_fill_(0, subset, True)
+    keep = mask[edge_index[0]] & mask[edge_index[1]]
+    ei = edge_index[:, keep]
+    if relabel_nodes:
+        remap = torch.cumsum(mask.long(), 0) - 1
+        ei = remap[ei]
+    return ei, (edge_attr[keep] if edge_attr is not None else None)
