@@ -37,6 +37,8 @@ def parse_irreps(spec) -> List[Tuple[int, int, int]]:
         for it in spec:
             if isinstance(it, str):
                 out += parse_irreps(it)
+            elif len(it) == 3:
+                out.append((int(it[0]), int(it[1]), int(it[2])))
             else:
                 mul, ir = it
                 if isinstance(ir, str):

@@ -1,0 +1,214 @@
+"""Pose initialisation and the reverse-diffusion sampler (utils/sampling.py) on the cb200 kernels.
+
+`sampling()` keeps the reference signature and contract (sampling.py:59-274): it mutates
+`data_list[i]['ligand'].pos` (device tensors), returns `(data_list, confidence)` with NaN -> -1000,
+asserts on the flags the reference asserts on, and lets exceptions propagate (callers halve the
+batch).  Per step the score-model forward and the pose update are cb200 kernels; the perturbation
+arithmetic of sampling.py:119-141 is folded into the K4 launch as scalar coefficients.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+import torch
+
+from .data import Batch, DataLoader
+from .diffusion_utils import LigandTopology, sde_step, set_time
+from .utils import crop_beyond
+
+
+def _is_iterable(x):
+    try:
+        iter(x)
+        return True
+    except TypeError:
+        return False
+
+
+def _mask_rotate_of(graph):
+    mr = graph["ligand"].mask_rotate
+    return mr[0] if isinstance(mr, (list, tuple)) else mr
+
+
+def randomize_position(data_list, no_torsion, no_random, tr_sigma_max, pocket_knowledge=False, pocket_cutoff=7):
+    """In-place pose initialisation (sampling.py:15-48): uniform torsions, random rotation about the
+    ligand centroid, placement on the pocket centre, N(0, tr_sigma_max) translation.  Host-side numpy /
+    scipy exactly like the reference (this is initialisation, not the per-step hot loop)."""
+    from scipy.spatial.transform import Rotation as R
+    center_pocket = data_list[0]["receptor"].pos.mean(dim=0)
+    if pocket_knowledge:
+        c = data_list[0]
+        d = torch.cdist(c["receptor"].pos, torch.from_numpy(c["ligand"].orig_pos[0]).float() - c.original_center)
+        label = torch.any(d < pocket_cutoff, dim=1)
+        if torch.any(label):
+            center_pocket = c["receptor"].pos[label].mean(dim=0)
+        else:
+            center_pocket = c["receptor"].pos[torch.argmin(torch.min(d, dim=1)[0])]
+    if not no_torsion:
+        for g in data_list:
+            n_tor = int(g["ligand"].edge_mask.sum())
+            updates = np.random.uniform(low=-np.pi, high=np.pi, size=n_tor)
+            bonds = g["ligand", "ligand"].edge_index.T[g["ligand"].edge_mask]
+            g["ligand"].pos = _twist_numpy(g["ligand"].pos, bonds, _mask_rotate_of(g), updates)
+    for g in data_list:
+        centre = torch.mean(g["ligand"].pos, dim=0, keepdim=True)
+        rot = torch.from_numpy(R.random().as_matrix()).float()
+        g["ligand"].pos = (g["ligand"].pos - centre) @ rot.T + center_pocket
+        if not no_random:
+            g["ligand"].pos += torch.normal(mean=0, std=tr_sigma_max, size=(1, 3))
+
+
+def _twist_numpy(pos, bonds, mask_rotate, updates):
+    """modify_conformer_torsion_angles (utils/torsion.py:48-72): sequential bond rotations on the host."""
+    from scipy.spatial.transform import Rotation as R
+    p = pos.detach().cpu().numpy().astype(np.float64).copy() if torch.is_tensor(pos) else np.array(pos, dtype=np.float64)
+    p = p.astype(np.float32) if torch.is_tensor(pos) else p
+    for k, e in enumerate(bonds.cpu().numpy()):
+        if updates[k] == 0:
+            continue
+        u, v = int(e[0]), int(e[1])
+        axis = p[u] - p[v]
+        axis = axis * updates[k] / np.linalg.norm(axis)
+        rot = R.from_rotvec(axis).as_matrix()
+        p[mask_rotate[k]] = (p[mask_rotate[k]] - p[v]) @ rot.T + p[v]
+    return torch.from_numpy(p.astype(np.float32))
+
+
+def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma,
+                      model_args, mask_rotate, noise_rows=None, no_random=False, ode=False, t_schedule=None,
+                      no_final_step_noise=False, temp_sampling=(1.0, 1.0, 1.0), temp_psi=(0.0, 0.0, 0.0),
+                      temp_sigma_data=0.5):
+    """The hot loop of sampling.py:93-223 on a batch that already lives on the device: `inference_steps` x
+    (score-model forward, K4 pose update).  Returns the final [B*N, 3] positions (also left in
+    batch['ligand'].pos).  No host synchronisation inside."""
+    b = batch.num_graphs
+    N = noise_rows if noise_rows is not None else b
+    batch_size = N
+    no_torsion = bool(model_args.no_torsion)
+    all_atoms = "all_atoms" in model_args and model_args.all_atoms
+    asyncronous_noise_schedule = False
+    g_const = {k: float(np.sqrt(np.float32(2 * np.log(getattr(model_args, f"{k}_sigma_max") / getattr(model_args, f"{k}_sigma_min")))))
+               for k in ("tr", "rot", "tor")}
+    if not _is_iterable(temp_sampling):
+        temp_sampling = [temp_sampling] * 3
+    if not _is_iterable(temp_psi):
+        temp_psi = [temp_psi] * 3
+    topo = LigandTopology(batch, mask_rotate, device)
+    pos = batch["ligand"].pos.float().contiguous()
+    batch["ligand"].pos = pos
+    for t_idx in range(inference_steps):
+        t_tr, t_rot, t_tor = tr_schedule[t_idx], rot_schedule[t_idx], tor_schedule[t_idx]
+        last = t_idx == inference_steps - 1
+        dt_tr = tr_schedule[t_idx] - tr_schedule[t_idx + 1] if not last else tr_schedule[t_idx]
+        dt_rot = rot_schedule[t_idx] - rot_schedule[t_idx + 1] if not last else rot_schedule[t_idx]
+        dt_tor = tor_schedule[t_idx] - tor_schedule[t_idx + 1] if not last else tor_schedule[t_idx]
+        tr_sigma, rot_sigma, tor_sigma = t_to_sigma(t_tr, t_rot, t_tor)
+        if hasattr(model_args, "crop_beyond") and model_args.crop_beyond is not None:
+            raise NotImplementedError("per-step crop_beyond for the score model is not in the shipped score YAML")
+        set_time(batch, t_schedule[t_idx] if t_schedule is not None else None, t_tr, t_rot, t_tor, b, all_atoms,
+                 asyncronous_noise_schedule, device)
+        tr_score, rot_score, tor_score = model(batch)[:3]
+
+        # sampling.py:119-167 -- g = sigma * sqrt(2 ln(smax/smin)); perturbation is linear in (score, z)
+        tr_g, rot_g, tor_g = tr_sigma * g_const["tr"], rot_sigma * g_const["rot"], tor_sigma * g_const["tor"]
+        noiseless = no_random or (no_final_step_noise and last)
+        nb = min(batch_size, N)
+        coeffs, zs = [], []
+        for k, (g, dt, temp, psi, sig, smax, smin, shape) in enumerate((
+                (tr_g, dt_tr, temp_sampling[0], temp_psi[0], tr_sigma, model_args.tr_sigma_max, model_args.tr_sigma_min, (nb, 3)),
+                (rot_g, dt_rot, temp_sampling[1], temp_psi[1], rot_sigma, model_args.rot_sigma_max, model_args.rot_sigma_min, (nb, 3)),
+                (tor_g, dt_tor, temp_sampling[2], temp_psi[2], tor_sigma, model_args.tor_sigma_max, model_args.tor_sigma_min, None))):
+            if k == 2 and no_torsion:
+                coeffs += [0.0, 0.0]
+                zs.append(None)
+                continue
+            if k == 2:
+                shape = tuple(tor_score.shape)
+            if ode:
+                c_s, c_n, z = 0.5 * g ** 2 * dt, 0.0, None
+            else:
+                z = None if noiseless else torch.normal(mean=0, std=1, size=shape, device=device)
+                c_s, c_n = g ** 2 * dt, g * np.sqrt(dt)
+                if temp != 1.0:
+                    sigma_data = np.exp(temp_sigma_data * np.log(smax) + (1 - temp_sigma_data) * np.log(smin))
+                    lam = (sigma_data + sig) / (sigma_data + sig / temp)
+                    c_s, c_n = g ** 2 * dt * (lam + temp * psi / 2), g * np.sqrt(dt * (1 + psi))
+            if z is not None and k < 2 and z.shape[0] != b:
+                raise RuntimeError(f"noise batch {z.shape[0]} != graphs in batch {b} (sampling.py:126-131: "
+                                   "batch_size must divide the number of samples)")
+            coeffs += [float(c_s), float(c_n)]
+            zs.append(z.float().contiguous() if z is not None else None)
+        sde_step(pos, topo, tr_score, rot_score, None if no_torsion else tor_score, coeffs, zs[0], zs[1], zs[2])
+
+    return pos
+
+
+def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,
+             no_random=False, ode=False, visualization_list=None, confidence_model=None, filtering_data_list=None,
+             filtering_model_args=None, asyncronous_noise_schedule=False, t_schedule=None, batch_size=32,
+             no_final_step_noise=False, pivot=None, return_full_trajectory=False, temp_sampling=1.0, temp_psi=0.0,
+             temp_sigma_data=0.5, return_features=False,
+             svgd_weight_log_0=None, svgd_repulsive_weight_log_0=None, svgd_weight_log_1=None,
+             svgd_repulsive_weight_log_1=None, svgd_kernel_size_log_0=None, svgd_kernel_size_log_1=None,
+             svgd_langevin_weight_log_0=None, svgd_langevin_weight_log_1=None, svgd_rot_log_rel_weight=0.0,
+             svgd_tor_log_rel_weight=0.0, svgd_use_x0=False):
+    N = len(data_list)
+    if return_features:
+        assert batch_size >= N, "Not implemented yet"
+    if svgd_weight_log_0 is not None and svgd_weight_log_1 is not None:
+        raise NotImplementedError("SVGD coupling (sampling.py:169-218) is an optional branch outside the hot path")
+    assert not (return_full_trajectory or return_features or pivot), "Not implemented yet in new inference version"
+    assert not asyncronous_noise_schedule
+
+    loader = DataLoader(data_list, batch_size=batch_size)
+    mask_rotate = _mask_rotate_of(data_list[0])
+    confidence = None
+    if confidence_model is not None:
+        filtering_loader = iter(DataLoader(filtering_data_list, batch_size=batch_size)) if filtering_data_list is not None else None
+        confidence = []
+    if not _is_iterable(temp_sampling):
+        temp_sampling = [temp_sampling] * 3
+    if not _is_iterable(temp_psi):
+        temp_psi = [temp_psi] * 3
+    assert len(temp_sampling) == 3 and len(temp_psi) == 3
+    no_torsion = bool(model_args.no_torsion)
+    all_atoms = "all_atoms" in model_args and model_args.all_atoms
+    g_const = {k: float(np.sqrt(np.float32(2 * np.log(getattr(model_args, f"{k}_sigma_max") / getattr(model_args, f"{k}_sigma_min")))))
+               for k in ("tr", "rot", "tor")}
+
+    with torch.no_grad():
+        for batch_id, batch in enumerate(loader):
+            b = batch.num_graphs
+            batch = batch.to(device)
+            pos = reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device,
+                                    t_to_sigma, model_args, mask_rotate, noise_rows=min(batch_size, N), no_random=no_random,
+                                    ode=ode, t_schedule=t_schedule, no_final_step_noise=no_final_step_noise,
+                                    temp_sampling=temp_sampling, temp_psi=temp_psi, temp_sigma_data=temp_sigma_data)
+            n = pos.shape[0] // b
+            for i in range(b):
+                data_list[batch_id * batch_size + i]["ligand"].pos = pos[i * n:n * (i + 1)]
+            if visualization_list is not None:
+                for idx, vis in enumerate(visualization_list):
+                    vis.add((data_list[idx]["ligand"].pos.detach().cpu() + data_list[idx].original_center.detach().cpu()),
+                            part=1, order=2)
+
+            if confidence_model is not None:
+                if filtering_data_list is not None:
+                    fb = next(filtering_loader)
+                    fb = fb.to(device)
+                    fb["ligand"].pos = pos
+                    if hasattr(filtering_model_args, "crop_beyond") and filtering_model_args.crop_beyond is not None:
+                        fb = crop_beyond(fb, filtering_model_args.crop_beyond, filtering_model_args.all_atoms)
+                    set_time(fb, 0, 0, 0, 0, b, filtering_model_args.all_atoms, asyncronous_noise_schedule, device)
+                    out = confidence_model(fb)
+                else:
+                    out = confidence_model(batch)
+                if type(out) is tuple:
+                    out = out[0]
+                confidence.append(out)
+
+    if confidence_model is not None:
+        confidence = torch.cat(confidence, dim=0)
+        confidence = torch.nan_to_num(confidence, nan=-1000)
+    return data_list, confidence

@@ -1,0 +1,232 @@
+"""TensorProductConvLayer on the fused K3 kernel, with the reference's parameter names.
+
+Mirrors models/tensor_layers.py:120-217 (`TensorProductConvLayer`), models/layers.py:8-15 (`FCBlock`)
+and e3nn.nn.BatchNorm (parameters `batch_norm.{weight,bias,running_mean,running_var}`), so a
+reference state_dict loads with strict=True (FasterTensorProduct has no parameters; e3nn's FCTP
+only carries constant buffers, which `TensorProductScoreModel` filters out on load).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .graph import EdgeList, static_edges
+from .irreps import (TPProgram, faster_tp_program, fctp_program, get_irrep_seq, irreps_dim, irreps_str,
+                     parse_irreps, sh_irreps)
+
+ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
+
+
+def FCBlock(in_dim, hidden_dim, out_dim, layers, dropout, activation="relu"):
+    """Linear-act-Dropout-(...)-Linear; Sequential indices 0/3 hold the Linears (layers.py:8-15)."""
+    act = ACTIVATIONS[activation]
+    assert layers >= 2
+    mods = [nn.Linear(in_dim, hidden_dim), act(), nn.Dropout(dropout)]
+    for _ in range(layers - 2):
+        mods += [nn.Linear(hidden_dim, hidden_dim), act(), nn.Dropout(dropout)]
+    mods += [nn.Linear(hidden_dim, out_dim)]
+    return nn.Sequential(*mods)
+
+
+def irrep_to_size(irrep: str) -> int:
+    return irreps_dim(irrep)
+
+
+class EquivariantBatchNorm(nn.Module):
+    """Parameter container + eval-mode affine of e3nn.nn.BatchNorm(irreps):
+    per irrep block, 0e channels subtract running_mean and add bias; every channel is scaled by
+    weight / sqrt(running_var + eps); 0o and l>0 channels have no mean / bias."""
+
+    def __init__(self, irreps, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.irreps = parse_irreps(irreps)
+        self.eps, self.momentum = eps, momentum
+        n_feat = sum(m for m, _, _ in self.irreps)
+        n_scalar = sum(m for m, l, p in self.irreps if l == 0 and p == 1)
+        self.register_buffer("running_mean", torch.zeros(n_scalar))
+        self.register_buffer("running_var", torch.ones(n_feat))
+        self.weight = nn.Parameter(torch.ones(n_feat))
+        self.bias = nn.Parameter(torch.zeros(n_scalar))
+        dims, is_s = [], []
+        for m, l, p in self.irreps:
+            dims += [2 * l + 1] * m
+            is_s += [l == 0 and p == 1] * m
+        self.register_buffer("_dims", torch.tensor(dims, dtype=torch.long), persistent=False)
+        self.register_buffer("_is_scalar", torch.tensor(is_s, dtype=torch.bool), persistent=False)
+
+    def affine(self):
+        """(scale[d], shift[d]) such that eval-mode BN(x) = x * scale + shift, per feature channel."""
+        scale_c = self.weight * torch.rsqrt(self.running_var + self.eps)
+        shift_c = torch.zeros_like(scale_c)
+        shift_c[self._is_scalar] = self.bias - self.running_mean * scale_c[self._is_scalar]
+        return (torch.repeat_interleave(scale_c, self._dims).contiguous(),
+                torch.repeat_interleave(shift_c, self._dims).contiguous())
+
+
+@dataclass
+class Segment:
+    """One edge list handled by one radial MLP (`fc[group]`) inside a layer call."""
+    edges: EdgeList
+    e_attr: torch.Tensor                 # [cap, ne]
+    sh: torch.Tensor                     # [cap, S]
+    group: int = 0
+    n0: int = 0                          # aggregation-node range [n0, n1) in the output rows
+    n1: int = 0
+    col_off: int = 0                     # offset of the neighbour node type inside x
+    e_post: Optional[torch.Tensor] = None  # [B, ne]
+
+
+class _DeviceProgram:
+    def __init__(self, prog: TPProgram, device):
+        self.prog = prog
+        self.rows = torch.from_numpy(prog.rows.view(np.uint8).copy()).to(device)
+        self.terms = torch.from_numpy(prog.terms.view(np.uint8).copy()).to(device)
+        self.out_ptr = torch.from_numpy(prog.out_ptr).to(device)
+        self.out_idx = torch.from_numpy(prog.out_idx).to(device)
+
+
+class TensorProductConvLayer(nn.Module):
+    def __init__(self, in_irreps, sh_irreps, out_irreps, n_edge_features, residual=True, batch_norm=True, dropout=0.0,
+                 hidden_features=None, faster=False, edge_groups=1, tp_weights_layers=2, activation="relu",
+                 depthwise=False):
+        super().__init__()
+        if depthwise:
+            raise NotImplementedError("depthwise convolutions are not used by the shipped configurations")
+        if tp_weights_layers != 2:
+            raise NotImplementedError("the fused kernel implements the 2-layer radial MLP of the shipped configurations")
+        if activation != "relu":
+            raise NotImplementedError("radial MLP activation must be relu")
+        self.in_irreps, self.out_irreps = irreps_str(in_irreps), irreps_str(out_irreps)
+        self.sh_irreps = irreps_str(sh_irreps)
+        self.residual, self.edge_groups, self.faster = residual, edge_groups, faster
+        self.out_size = irreps_dim(out_irreps)
+        self.n_edge_features = n_edge_features
+        hidden_features = hidden_features or n_edge_features
+        self.hidden_features = hidden_features
+        if faster:
+            assert self.sh_irreps == "1x0e + 1x1o", "sh_irreps don't look like 1st order spherical harmonics"
+            self.program = faster_tp_program(self.in_irreps, self.out_irreps)
+        else:
+            self.program = fctp_program(self.in_irreps, self.sh_irreps, self.out_irreps)
+        self.weight_numel = self.program.weight_numel
+        if edge_groups == 1:
+            self.fc = FCBlock(n_edge_features, hidden_features, self.weight_numel, tp_weights_layers, dropout, activation)
+        else:
+            self.fc = nn.ModuleList([FCBlock(n_edge_features, hidden_features, self.weight_numel, tp_weights_layers,
+                                             dropout, activation) for _ in range(edge_groups)])
+        self.batch_norm = EquivariantBatchNorm(out_irreps) if batch_norm else None
+        self._dev_prog = None
+
+    # ------------------------------------------------------------------ helpers
+    def _fc(self, g):
+        return self.fc if self.edge_groups == 1 else self.fc[g]
+
+    def device_program(self, device):
+        if self._dev_prog is None or self._dev_prog.rows.device != device:
+            self._dev_prog = _DeviceProgram(self.program, device)
+        return self._dev_prog
+
+    def _check_mode(self):
+        if self.training and (self.batch_norm is not None or any(
+                isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules())):
+            raise NotImplementedError(
+                "cb200 TensorProductConvLayer runs the inference path (eval mode: running-stat BatchNorm, no dropout); "
+                "call model.eval() before sampling")
+
+    # ------------------------------------------------------------------ fused path
+    def run(self, x, segments: List[Segment], n_out, ns, e_cols, agg_cols=None, nbr_cols=None,
+            agg_scalars=None, agg_graph=None, residual=None):
+        """x [N_in, d_in]; returns [n_out, d_out].
+
+        e_cols / agg_cols / nbr_cols: (offset, width) of the edge-embedding, aggregation-side and
+        neighbour-side scalar blocks inside the first Linear's input (tensor_layers.py:201-202 applied
+        to the concatenations built at score_model.py:290-291,314,367-368,397,439-440).
+        agg_scalars: [n_out, ns] table for the aggregation side (defaults to x[:, :ns])."""
+        self._check_mode()
+        dev = x.device
+        P = self.program
+        dp = self.device_program(dev)
+        H = self.hidden_features
+        groups = sorted({s.group for s in segments})
+        # node-level projections of the first Linear (plain GEMM: plumbing)
+        xs = x[:, :ns]
+        P_nbr, P_agg = {}, {}
+        if nbr_cols is not None:
+            Wn = torch.cat([self._fc(g)[0].weight[:, nbr_cols[0]:nbr_cols[0] + nbr_cols[1]] for g in groups], 0)
+            pn = (xs @ Wn.t()).contiguous()
+            for k, g in enumerate(groups):
+                P_nbr[g] = (pn, k * H)
+        if agg_cols is not None:
+            Wa = torch.cat([self._fc(g)[0].weight[:, agg_cols[0]:agg_cols[0] + agg_cols[1]] for g in groups], 0)
+            src = xs if agg_scalars is None else agg_scalars
+            pa = (src @ Wa.t()).contiguous()
+            for k, g in enumerate(groups):
+                P_agg[g] = (pa, k * H)
+        out = torch.empty((n_out, P.d_out), dtype=torch.float32, device=dev)
+        a = _lib.TpConvArgs()
+        a.x = _lib.f32(x, "x")
+        a.d_in, a.d_out, a.S = x.shape[1], P.d_out, P.sh_dim
+        assert x.shape[1] == P.d_in, f"node feature width {x.shape[1]} != {P.d_in}"
+        a.ne, a.H, a.n_out = e_cols[1], H, n_out
+        a.agg_graph = _lib.i32(agg_graph, "agg_graph", allow_none=True)
+        a.rows, a.n_rows = dp.rows.data_ptr(), P.n_rows
+        a.terms, a.n_terms = dp.terms.data_ptr(), len(P.terms)
+        a.out_ptr, a.out_idx, a.n_slots = dp.out_ptr.data_ptr(), dp.out_idx.data_ptr(), P.n_slots
+        a.n_segs = len(segments)
+        keep = []
+        for k, s in enumerate(segments):
+            fc = self._fc(s.group)
+            W1, b1, W2, b2 = fc[0].weight, fc[0].bias, fc[3].weight, fc[3].bias
+            sg = a.segs[k]
+            sg.rowptr, sg.col = _lib.i32(s.edges.rowptr, "rowptr"), _lib.i32(s.edges.col, "col")
+            sg.e_attr, sg.sh = _lib.f32(s.e_attr, "e_attr"), _lib.f32(s.sh, "sh")
+            assert s.e_attr.shape[1] == e_cols[1] and s.sh.shape[1] == P.sh_dim
+            sg.e_post = _lib.f32(s.e_post, "e_post", allow_none=True)
+            if s.group in P_agg:
+                t, off = P_agg[s.group]
+                sg.P_agg, sg.ldp_agg = t.data_ptr() + 4 * off, t.shape[1]
+            if s.group in P_nbr:
+                t, off = P_nbr[s.group]
+                sg.P_nbr, sg.ldp_nbr = t.data_ptr() + 4 * off, t.shape[1]
+            sg.W1e, sg.ldw1 = _lib.f32(W1, "W1") + 4 * e_cols[0], W1.shape[1]
+            sg.b1, sg.W2, sg.b2 = _lib.f32(b1, "b1"), _lib.f32(W2, "W2"), _lib.f32(b2, "b2")
+            sg.n0, sg.n1, sg.col_off = s.n0, s.n1, s.col_off
+        if self.batch_norm is not None:
+            scale, shift = self.batch_norm.affine()
+            a.bn_scale, a.bn_shift = scale.data_ptr(), shift.data_ptr()
+            keep += [scale, shift]
+        if residual is not None:
+            a.residual, a.d_res, a.ld_res = _lib.f32(residual, "residual"), min(residual.shape[1], P.d_out), residual.shape[1]
+        a.out = out.data_ptr()
+        _lib.tp_conv_forward(a)
+        return out
+
+    # ------------------------------------------------------------------ reference-style call
+    def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce="mean", edge_weight=1.0):
+        """Drop-in for tensor_layers.py:195-217 with explicit (already concatenated) edge features.
+        edge_attr is a tensor (edge_groups == 1) or a list with one tensor per edge group."""
+        assert reduce == "mean"
+        if not (isinstance(edge_weight, (int, float)) and float(edge_weight) == 1.0):
+            raise NotImplementedError("smooth_edges edge weights are not used by the shipped configurations")
+        n_out = int(out_nodes or node_attr.shape[0])
+        if edge_index.shape[1] == 0:
+            out = torch.zeros((n_out, self.out_size), dtype=node_attr.dtype, device=node_attr.device)
+        else:
+            attrs = [edge_attr] if self.edge_groups == 1 else list(edge_attr)
+            segs, start = [], 0
+            for g, ea in enumerate(attrs):
+                n = ea.shape[0]
+                ei = edge_index[:, start:start + n]
+                el, perm = static_edges(ei, n_out)
+                segs.append(Segment(el, ea[perm].contiguous(), edge_sh[start:start + n][perm].contiguous(), g, 0, n_out))
+                start += n
+            out = self.run(node_attr.contiguous(), segs, n_out, 0, (0, self.n_edge_features))
+        if self.residual:
+            out = out + torch.nn.functional.pad(node_attr[:n_out], (0, out.shape[-1] - node_attr.shape[-1]))
+        return out

@@ -1,0 +1,106 @@
+"""Shared test helpers: graph (de)serialisation, model construction, BN randomisation, noise injection."""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+from argparse import Namespace
+from contextlib import contextmanager
+from functools import partial
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from confidence_bootstrapping_b200.data import Batch, HeteroData  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+_EDGE_TYPES = [("ligand", "lig_bond", "ligand"), ("receptor", "rec_contact", "receptor"),
+               ("atom", "atom_contact", "atom"), ("atom", "atom_rec_contact", "receptor")]
+
+
+def pack_graph(g) -> dict:
+    d = {"nodes": {}, "edges": {}, "graph": {}}
+    for nt in g.node_types:
+        d["nodes"][nt] = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in g[nt].items()
+                          if torch.is_tensor(v) or isinstance(v, np.ndarray)}
+    for et in g.edge_types:
+        d["edges"]["|".join(et)] = {k: v for k, v in g[et].items() if torch.is_tensor(v)}
+    d["graph"]["original_center"] = g.original_center
+    return d
+
+
+def unpack_graph(d) -> HeteroData:
+    g = HeteroData()
+    for nt, attrs in d["nodes"].items():
+        for k, v in attrs.items():
+            if k in ("mask_rotate", "orig_pos"):
+                v = v.numpy()
+            setattr(g[nt], k, v)
+    for et, attrs in d["edges"].items():
+        for k, v in attrs.items():
+            setattr(g[tuple(et.split("|"))], k, v)
+    g.original_center = d["graph"]["original_center"]
+    return g
+
+
+def small_score_args(**kw) -> Namespace:
+    """A tiny CG score configuration (fast on CPU, exercises every code path of the shipped one)."""
+    from confidence_bootstrapping_b200.configs import score_model_args
+    base = dict(ns=8, nv=2, num_conv_layers=2, num_prot_emb_layers=1, moad_esm_embeddings_path=None)
+    base.update(kw)
+    return score_model_args(**base)
+
+
+def randomize_norm_stats(model, seed=0):
+    """Make every BatchNorm non-trivial (fresh modules have mean 0 / var 1 / weight 1 / bias 0)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in model.modules():
+            if hasattr(m, "running_var") and torch.is_tensor(getattr(m, "running_var", None)):
+                dev = m.running_var.device
+                m.running_var.copy_((torch.rand(m.running_var.shape, generator=g) + 0.5).to(dev))
+                if m.running_mean.numel():
+                    m.running_mean.copy_((torch.randn(m.running_mean.shape, generator=g) * 0.2).to(dev))
+                if getattr(m, "weight", None) is not None:
+                    m.weight.copy_((torch.rand(m.weight.shape, generator=g) + 0.5).to(dev))
+                if getattr(m, "bias", None) is not None and m.bias.numel():
+                    m.bias.copy_((torch.randn(m.bias.shape, generator=g) * 0.2).to(dev))
+
+
+class NoiseTape:
+    """Deterministic replacement for torch.normal: the k-th call returns the k-th recorded/seeded draw
+    (always generated on the CPU, then moved), so CPU oracle, real reference and CUDA product see the
+    same noise (sampling.py:126-141 draws with torch.normal on `device`)."""
+
+    def __init__(self, seed=0):
+        self.gen = torch.Generator().manual_seed(seed)
+        self.calls = 0
+
+    def __call__(self, mean=0, std=1, size=None, device=None, **kw):
+        self.calls += 1
+        z = torch.randn(tuple(size), generator=self.gen) * std + mean
+        return z.to(device) if device is not None else z
+
+
+@contextmanager
+def injected_noise(seed=0):
+    tape, orig = NoiseTape(seed), torch.normal
+    torch.normal = tape
+    try:
+        yield tape
+    finally:
+        torch.normal = orig
+
+
+def rmsd(a, b):
+    return (a.detach().cpu().double() - b.detach().cpu().double()).pow(2).sum(-1).mean().sqrt().item()
+
+
+def rel_err(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()

@@ -1,0 +1,133 @@
+"""End-to-end parity of the cb200 score model and sampler against the CPU oracle / reference goldens."""
+import copy
+import os
+from argparse import Namespace
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, injected_noise, randomize_norm_stats, rel_err, rmsd, small_score_args, unpack_graph
+from oracle import model as om, sampler as osamp
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(args, seed=0):
+    from confidence_bootstrapping_b200 import so3, torus
+    from confidence_bootstrapping_b200.diffusion_utils import t_to_sigma as t2s_full
+    from confidence_bootstrapping_b200.utils import get_model
+    t2s = partial(t2s_full, args=args)
+    torch.manual_seed(seed)
+    model = get_model(args, torch.device("cuda"), t_to_sigma=t2s, no_parallel=True)
+    randomize_norm_stats(model, seed=seed + 1)
+    model.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    hp = om.hyper_from_args(args)
+    oracle_fwd = lambda b: om.cg_forward(sd, hp, b, partial(osamp.t_to_sigma, args=args), so3.score_norm, torus.score_norm)
+    return model, t2s, oracle_fwd
+
+
+def test_golden_small_model_forward_and_sampling():
+    """Reference-produced golden (real models/score_model.py + utils/sampling.py on CPU): forward outputs
+    to 1e-5 relative, final poses to 1e-3 A (BASELINE.json)."""
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule, set_time, t_to_sigma as t2s_full
+    from confidence_bootstrapping_b200.sampling import sampling
+    from confidence_bootstrapping_b200.utils import get_model
+    g = torch.load(os.path.join(GOLDEN, "score_small.pt"), weights_only=False)
+    args = Namespace(**g["args"])
+    t2s = partial(t2s_full, args=args)
+    dev = torch.device("cuda")
+    model = get_model(args, dev, t_to_sigma=t2s, no_parallel=True)
+    model.load_state_dict(g["state_dict"], strict=True)
+    model.eval()
+    batch = Batch.from_data_list([unpack_graph(x) for x in g["graphs"]]).to(dev)
+    set_time(batch, None, g["t"], g["t"], g["t"], 2, False, False, dev)
+    with torch.no_grad():
+        tr, rot, tor, side = model(batch)
+    assert side is None
+    for got, want in ((tr, g["tr"]), (rot, g["rot"]), (tor, g["tor"])):
+        assert got.shape == want.shape and rel_err(got, want) < 1e-5
+    base = Batch.from_data_list([unpack_graph(g["graphs"][1])])
+    data_list = []
+    for s in g["sample_start"]:
+        d = copy.deepcopy(base)
+        d["ligand"].pos = s.clone()
+        data_list.append(d)
+    sched = get_t_schedule("expbeta", g["sample_steps"], 1, 1)
+    with injected_noise(seed=g["sample_noise_seed"]):
+        out, conf = sampling(data_list=data_list, model=model, inference_steps=g["sample_steps"], tr_schedule=sched,
+                             rot_schedule=sched, tor_schedule=sched, device=dev, t_to_sigma=t2s, model_args=args, batch_size=4)
+    assert conf is None
+    for d, want in zip(out, g["sample_final"]):
+        assert d["ligand"].pos.is_cuda
+        assert rmsd(d["ligand"].pos, want) < 1e-3
+
+
+@pytest.mark.parametrize("sizes", [[(60, 14)], [(90, 23), (48, 9), (120, 31)]])
+def test_full_size_score_model_vs_oracle(sizes):
+    """Shipped hyper-parameters (ns 32, nv 6, 3+5 layers, lmax 1, 1280-d LM features), seeded random weights."""
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import set_time
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    args = score_model_args()
+    model, t2s, oracle_fwd = _build(args)
+    graphs = [make_complex(40 + i, nr, nl, all_atoms=False) for i, (nr, nl) in enumerate(sizes)]
+    for t in (1.0, 0.35):
+        cpu = Batch.from_data_list(copy.deepcopy(graphs))
+        osamp.set_time(cpu, t, t, t, len(graphs))
+        gpu = Batch.from_data_list(copy.deepcopy(graphs)).to("cuda")
+        set_time(gpu, None, t, t, t, len(graphs), False, False, torch.device("cuda"))
+        with torch.no_grad():
+            want = oracle_fwd(cpu)
+            got = model(gpu)
+        for a, b, name in zip(got[:3], want[:3], ("tr", "rot", "tor")):
+            assert a.shape == b.shape, name
+            assert rel_err(a, b) < 2e-5, (name, t, rel_err(a, b))
+
+
+def test_sampling_vs_oracle_full_size():
+    """20 reverse-diffusion steps with identical injected noise: poses within 1e-3 A RMSD of the CPU oracle."""
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule
+    from confidence_bootstrapping_b200.sampling import randomize_position, sampling
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    args = score_model_args()
+    model, t2s, oracle_fwd = _build(args, seed=3)
+    g = Batch.from_data_list([make_complex(77, 80, 16, all_atoms=False)])
+    np.random.seed(0)
+    torch.manual_seed(0)
+    dl = [copy.deepcopy(g) for _ in range(4)]
+    randomize_position(dl, False, False, args.tr_sigma_max)
+    dl_cpu = copy.deepcopy(dl)
+    steps = 20
+    sched = get_t_schedule("expbeta", steps, 1, 1)
+    with injected_noise(seed=9):
+        out, _ = sampling(data_list=dl, model=model, inference_steps=steps, tr_schedule=sched, rot_schedule=sched,
+                          tor_schedule=sched, device=torch.device("cuda"), t_to_sigma=t2s, model_args=args, batch_size=4)
+    with injected_noise(seed=9):
+        ref, _ = osamp.sampling(dl_cpu, oracle_fwd, steps, sched, sched, sched, partial(osamp.t_to_sigma, args=args), args, batch_size=4)
+    for a, b in zip(out, ref):
+        assert rmsd(a["ligand"].pos, b["ligand"].pos) < 1e-3
+    # ragged last batch raises like the reference (sampling.py:126-131)
+    with pytest.raises(Exception):
+        sampling(data_list=[copy.deepcopy(g) for _ in range(3)], model=model, inference_steps=2, tr_schedule=sched,
+                 rot_schedule=sched, tor_schedule=sched, device=torch.device("cuda"), t_to_sigma=t2s, model_args=args, batch_size=2)
+
+
+def test_model_refuses_training_mode():
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import set_time
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    args = small_score_args()
+    model, _, _ = _build(args)
+    model.train()
+    b = Batch.from_data_list([make_complex(1, 30, 8, all_atoms=False, lm_dim=0)]).to("cuda")
+    set_time(b, None, 0.5, 0.5, 0.5, 1, False, False, torch.device("cuda"))
+    with pytest.raises(NotImplementedError):
+        model(b)

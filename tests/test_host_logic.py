@@ -1,0 +1,126 @@
+"""CPU-side checks of the product's host logic: TP programs (irreps.py), C-ABI surface, containers."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT
+from oracle import model as om, o3
+from confidence_bootstrapping_b200 import _lib, irreps
+from confidence_bootstrapping_b200.data import Batch
+from confidence_bootstrapping_b200.synthetic import make_complex, rotatable_bond_masks
+
+
+def eval_program(P, x, sh, w):
+    """Reference evaluator of a TPProgram on the CPU (float64): out = sum_rows f_r * w[w_base+m]."""
+    x, sh, w = x.double().numpy(), sh.double().numpy(), w.double().numpy()
+    out = np.zeros((x.shape[0], P.d_out))
+    for r in P.rows:
+        f = np.zeros(x.shape[0])
+        for t in P.terms[r["term_begin"]: r["term_end"]]:
+            f += t["coef"].astype(np.float64) * x[:, t["x_idx"]] * sh[:, t["sh_idx"]]
+        for m in range(r["mul"]):
+            out[:, r["out_base"] + m * r["out_step"]] += f * w[:, r["w_base"] + m]
+    return torch.from_numpy(out)
+
+
+SEQ = ["32x0e", "32x0e + 6x1o", "32x0e + 6x1o + 6x1e", "32x0e + 6x1o + 6x1e + 6x0o"]
+
+
+@pytest.mark.parametrize("i_in,i_out,numel,rows", [(0, 1, 1216, 128), (1, 2, 1480, 170), (2, 3, 1588, 212), (3, 3, 1660, 236)])
+def test_faster_program_equals_oracle(i_in, i_out, numel, rows):
+    P = irreps.faster_tp_program(SEQ[i_in], SEQ[i_out])
+    assert P.weight_numel == numel == om.faster_weight_numel(SEQ[i_in], SEQ[i_out])
+    assert P.n_rows == rows
+    torch.manual_seed(0)
+    x, sh, w = torch.randn(4, P.d_in), torch.randn(4, 4), torch.randn(4, numel)
+    want = om.faster_tensor_product(SEQ[i_in], SEQ[i_out], x.double(), sh.double(), w.double())
+    assert torch.allclose(eval_program(P, x, sh, w), want, atol=1e-6)
+
+
+CONF = ["24x0e", "24x0e + 6x1o", "24x0e + 6x1o + 6x1e", "24x0e + 6x1o + 6x1e + 24x0o"]
+
+
+@pytest.mark.parametrize("in_ir,sh_ir,out_ir,numel", [
+    (CONF[0], "1x0e + 1x1o + 1x2e", CONF[1], 720), (CONF[1], "1x0e + 1x1o + 1x2e", CONF[2], 972),
+    (CONF[2], "1x0e + 1x1o + 1x2e", CONF[3], 1224), (CONF[3], "1x0e + 1x1o + 1x2e", CONF[3], 1944),
+    (SEQ[3], "1x0e + 1x1o", "2x1o + 2x1e", 124), (SEQ[3], "1x1o", "32x0o + 32x0e", 384)])
+def test_fctp_program_equals_oracle(in_ir, sh_ir, out_ir, numel):
+    P = irreps.fctp_program(in_ir, sh_ir, out_ir)
+    tp = o3.FullyConnectedTensorProduct(in_ir, sh_ir, out_ir)
+    assert P.weight_numel == numel == tp.weight_numel
+    torch.manual_seed(1)
+    x, sh, w = torch.randn(3, P.d_in), torch.randn(3, P.sh_dim), torch.randn(3, numel)
+    assert torch.allclose(eval_program(P, x, sh, w), tp(x.double(), sh.double(), w.double()), atol=1e-6)
+    assert P.n_rows <= 320 and P.out_ptr[-1] == P.n_slots == sum(r["mul"] for r in P.rows)
+
+
+def test_full_tp_1o_block_matches_oracle():
+    dim, off, w = irreps.full_tp_1o_block(1)
+    ftp = o3.FullTensorProduct("1x0e + 1x1o", "2e")
+    assert dim == ftp.irreps_out.dim == 20 and off == 0
+    torch.manual_seed(2)
+    sh, y2 = torch.randn(5, 4).double(), torch.randn(5, 5).double()
+    want = ftp(sh, y2)[:, :3]
+    got = torch.einsum("ijk,ei,ej->ek", torch.from_numpy(w), sh[:, 1:4], y2)
+    assert torch.allclose(got, want, atol=1e-12)
+
+
+def test_wigner_matches_oracle():
+    for ls in [(1, 1, 0), (1, 1, 1), (1, 1, 2), (1, 2, 1), (2, 2, 2), (0, 2, 2)]:
+        assert np.allclose(irreps.wigner_3j(*ls), o3.wigner_3j(*ls).numpy(), atol=1e-12)
+
+
+def test_cabi_exports_and_struct_layout():
+    """The shared library loads, exports every symbol include/cb200.h declares, and the ctypes mirrors
+    have the C sizes (no compute call: this runs without a GPU)."""
+    header = open(os.path.join(ROOT, "include", "cb200.h")).read()
+    declared = set(re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", header)) - {"cb_tp_conv_args", "cb_edge_feat_args"}
+    lib = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in cb200.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert lib.cb_version() >= 100
+    for which, struct in enumerate([_lib.EdgeFeatArgs, _lib.TpSegment, _lib.TpConvArgs, _lib.SdeStepArgs]):
+        assert lib.cb_sizeof(which) == ctypes.sizeof(struct)
+    assert lib.cb_sizeof(4) == irreps.ROW_DTYPE.itemsize and lib.cb_sizeof(5) == irreps.TERM_DTYPE.itemsize
+
+
+def test_wrappers_refuse_cpu_tensors():
+    """No CPU fallback: handing host tensors to a kernel wrapper is an error, not a slow path."""
+    t = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        _lib.f32(t, "x")
+
+
+def test_batch_collate_and_split_roundtrip():
+    gs = [make_complex(s, 20 + 5 * s, 6 + s, all_atoms=True, lm_dim=4) for s in range(3)]
+    b = Batch.from_data_list(gs)
+    assert b.num_graphs == 3
+    assert b["ligand"].batch.tolist() == sum([[i] * g["ligand"].num_nodes for i, g in enumerate(gs)], [])
+    off = 0
+    for i, g in enumerate(gs):
+        n = g["receptor"].num_nodes
+        e = b["receptor", "receptor"].edge_index
+        sel = (b["receptor"].batch[e[0]] == i)
+        assert torch.equal(e[:, sel] - off, g["receptor", "receptor"].edge_index)
+        off += n
+    for g, h in zip(gs, b.to_data_list()):
+        assert torch.equal(g["atom", "receptor"].edge_index, h["atom", "receptor"].edge_index)
+        assert torch.equal(g["ligand"].pos, h["ligand"].pos)
+    # nested collate of 1-graph batches (how the reference's callers build data_list, sampling.py:78)
+    nested = Batch.from_data_list([Batch.from_data_list([gs[0]]), Batch.from_data_list([gs[0]])])
+    assert nested.num_graphs == 2 and nested["ligand"].num_nodes == 2 * gs[0]["ligand"].num_nodes
+
+
+def test_rotatable_masks_orientation():
+    g = make_complex(4, 30, 18, all_atoms=False, lm_dim=0)
+    ei = g["ligand", "ligand"].edge_index.T.numpy()
+    me, mr = rotatable_bond_masks(g["ligand"].num_nodes, ei)
+    assert mr.shape == (me.sum(), g["ligand"].num_nodes) and me.sum() > 0
+    for k, (u, v) in enumerate(ei[me]):
+        assert not mr[k, u] and mr[k, v]          # utils/torsion.py:81-82
+        assert 1 < mr[k].sum() <= g["ligand"].num_nodes // 2 + 1
