@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the reverse-diffusion pose-sampling hot path (BASELINE.json metric: sampled poses/sec).
+
+  python bench.py --gpus N --steps K --warmup W            # cb200 arm (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   # reference arm: CPU restatement on the host cores
+
+One "step" = one full pass of the hot path over one batch: `samples` poses of one synthetic complex,
+`inference_steps` reverse-diffusion steps each (score-model forward + SDE update), then confidence scoring.
+Workload = BASELINE.json configs[1] (400-residue pocket, 40-atom ligand, 40 samples x 20 steps).
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from functools import partial
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RES, N_LIG, SAMPLES, INF_STEPS = 400, 40, 40, 20
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def build_workload(seed, args_ns, samples):
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.sampling import randomize_position
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    g = Batch.from_data_list([make_complex(seed, N_RES, N_LIG, all_atoms=True)])
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    data_list = [copy.deepcopy(g) for _ in range(samples)]
+    randomize_position(data_list, args_ns.no_torsion, False, args_ns.tr_sigma_max)
+    return data_list
+
+
+def host_bytes(data_list):
+    n = 0
+    for d in data_list:
+        for store in d._stores.values():
+            for v in store._d.values():
+                if torch.is_tensor(v):
+                    n += v.numel() * v.element_size()
+    return n
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def run_reference(opts):
+    """The reference's own CPU implementation of the path.  The real stack (e3nn / torch_cluster / torch_scatter /
+    PyG) is not installable offline, so this is the reference-equivalent restatement (oracle/, kind 'port') in the
+    reference formulation, with all host threads.  Each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from confidence_bootstrapping_b200 import so3, torus
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule
+    from confidence_bootstrapping_b200.utils import get_model
+    from confidence_bootstrapping_b200.diffusion_utils import t_to_sigma
+    from oracle import model as om, sampler as osamp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    args_ns = score_model_args()
+    torch.manual_seed(0)
+    model = get_model(args_ns, torch.device("cpu"), t_to_sigma=partial(t_to_sigma, args=args_ns), no_parallel=True).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    hp = om.hyper_from_args(args_ns)
+    t2s = partial(osamp.t_to_sigma, args=args_ns)
+    fwd = lambda b: om.cg_forward(sd, hp, b, t2s, so3.score_norm, torus.score_norm)
+    n_s, n_steps = opts.ref_samples, opts.ref_inf_steps
+    sched = get_t_schedule("expbeta", INF_STEPS, 1, 1)[:: max(1, INF_STEPS // n_steps)][:n_steps]
+    times = []
+    for it in range(opts.warmup + opts.steps):
+        dl = build_workload(100 + it, args_ns, n_s)
+        t0 = time.perf_counter()
+        osamp.sampling(dl, fwd, n_steps, sched, sched, sched, t2s, args_ns, batch_size=n_s)
+        dt = time.perf_counter() - t0
+        if it >= opts.warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    # a full workload step is SAMPLES poses x INF_STEPS steps: scale the bounded sample linearly
+    full = per_step * (SAMPLES / n_s) * (INF_STEPS / n_steps)
+    value = SAMPLES / full
+    sample = f"{n_s} poses x {n_steps} of {INF_STEPS} reverse steps per step, score model only, scaled linearly"
+    print(json.dumps({
+        "impl": "reference", "metric": "sampled poses/sec", "value": value, "unit": "poses/s", "n_gpus": opts.gpus,
+        "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(False),
+        "cpu_baseline": {"value": value, "unit": "poses/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(confidence):
+    return {"workload": f"configs[1]: 1 synthetic complex ({N_RES}-residue pocket, {N_LIG}-atom ligand), {SAMPLES} samples x "
+                        f"{INF_STEPS} reverse-diffusion steps" + (" + confidence scoring" if confidence else " (score model)"),
+            "n_residues": N_RES, "n_ligand_atoms": N_LIG, "samples": SAMPLES, "inference_steps": INF_STEPS,
+            "confidence_scoring": bool(confidence), "l2": "flushed between timed steps (256 MiB write)",
+            "weights": "seeded random init (checkpoints unavailable offline)"}
+
+
+# ----------------------------------------------------------------------------------------- cb200 arm
+class TpTimer:
+    """CUDA-event timing + algorithmic byte/FLOP accounting of every K3 launch in the timed region."""
+
+    def __init__(self):
+        self.records = []
+
+    @contextlib.contextmanager
+    def __call__(self, a):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        self.records.append((s, e, a._meta, a.d_in, a.d_out, a.ne, a.S, a.H))
+
+    def summarise(self):
+        tot_ms, tot_bytes, tot_flops_ref, tot_flops_exec, n = 0.0, 0.0, 0.0, 0.0, 0
+        counters = {}
+        for (_, _, meta, *_r) in self.records:
+            for c in meta["edge_counters"]:
+                counters[c.data_ptr()] = c
+        for (s, e, meta, d_in, d_out, ne, S, H) in self.records:
+            layer = meta["layer"]
+            E = [int(c.item()) for c in meta["edge_counters"]]
+            numel, K1 = layer.weight_numel, layer.n_edge_features
+            params = len(meta["groups"]) * (H * K1 + H + numel * H + numel)
+            R = layer.program.n_rows
+            tot_bytes += 4.0 * (meta["n_in"] * d_in + meta["n_out"] * d_out) + sum(E) * (4.0 * ne + 4.0 * S + 8.0) + 4.0 * params
+            slots = layer.program.n_slots
+            tot_flops_ref += sum(E) * 2.0 * (K1 * H + H * numel + slots)
+            tot_flops_exec += sum(E) * 2.0 * (ne * H + R * (H + 1)) + 2.0 * meta["n_out"] * len(E) * slots * (H + 1)
+            tot_ms += s.elapsed_time(e)
+            n += 1
+        return dict(launches=n, ms=tot_ms, bytes=tot_bytes, flops_ref=tot_flops_ref, flops_exec=tot_flops_exec)
+
+
+def run_cb200(opts):
+    import torch.distributed as dist
+    from confidence_bootstrapping_b200 import _lib
+    from confidence_bootstrapping_b200.configs import confidence_model_args, score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule, t_to_sigma
+    from confidence_bootstrapping_b200.sampling import _mask_rotate_of, reverse_diffusion, sampling
+    from confidence_bootstrapping_b200.utils import get_model
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (cb200 arm) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args_ns = score_model_args()
+    t2s = partial(t_to_sigma, args=args_ns)
+    torch.manual_seed(0)
+    model = get_model(args_ns, dev, t_to_sigma=t2s, no_parallel=True).eval()
+    conf_model, conf_args = None, None
+    if not opts.no_confidence:
+        try:
+            conf_args = confidence_model_args()
+            conf_model = get_model(conf_args, dev, t_to_sigma=t2s, no_parallel=True, confidence_mode=True).eval()
+        except NotImplementedError:
+            conf_model, conf_args = None, None
+    sched = get_t_schedule("expbeta", INF_STEPS, 1, 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    kw = dict(model=model, inference_steps=INF_STEPS, tr_schedule=sched, rot_schedule=sched, tor_schedule=sched, device=dev,
+              t_to_sigma=t2s, model_args=args_ns, batch_size=SAMPLES)
+
+    def e2e_step(seed):
+        """Public API with HOST buffers: H2D of the batch, 20 steps, confidence, D2H of poses + confidences."""
+        dl = build_workload(seed, args_ns, SAMPLES)
+        fl = copy.deepcopy(dl) if conf_model is not None else None
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out, conf = sampling(data_list=dl, confidence_model=conf_model, filtering_data_list=fl, filtering_model_args=conf_args, **kw)
+        poses = torch.stack([d["ligand"].pos for d in out]).cpu()
+        c = conf.cpu() if conf is not None else None
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h2d = host_bytes(dl) + (host_bytes(fl) if fl is not None else 0)
+        d2h = poses.numel() * 4 + (c.numel() * 4 if c is not None else 0)
+        return dt, h2d, d2h
+
+    def resident_step(batch, fbatch):
+        """Inputs already in HBM: the 20-step loop + confidence scoring, timed with CUDA events."""
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        with torch.no_grad():
+            pos = reverse_diffusion(batch, model, INF_STEPS, sched, sched, sched, dev, t2s, args_ns, mask_rotate)
+            if conf_model is not None:
+                from confidence_bootstrapping_b200.diffusion_utils import set_time
+                from confidence_bootstrapping_b200.utils import crop_beyond
+                fbatch["ligand"].pos = pos
+                fb = crop_beyond(fbatch, conf_args.crop_beyond, True) if conf_args.crop_beyond is not None else fbatch
+                set_time(fb, 0, 0, 0, 0, fb.num_graphs, True, False, dev)
+                conf_model(fb)
+        e.record()
+        return s, e
+
+    # each rank owns its own complex (weak scaling: the complex list is sharded, no data-path collective)
+    base_seed = 1000 * (rank + 1)
+    for w in range(opts.warmup):
+        e2e_step(base_seed + w)
+    dl = build_workload(base_seed + 500, args_ns, SAMPLES)
+    mask_rotate = _mask_rotate_of(dl[0])
+    batches = [(Batch.from_data_list(copy.deepcopy(dl)).to(dev), Batch.from_data_list(copy.deepcopy(dl)).to(dev) if conf_model is not None else None)
+               for _ in range(opts.steps)]
+    for b in batches[:1]:
+        resident_step(copy.deepcopy(b[0]), copy.deepcopy(b[1]))       # warm the resident path too
+    timer = TpTimer()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count
+    events = []
+    with ClockSampler(local) as clocks:
+        _lib.tp_conv_hook = timer
+        for b, fb in batches:
+            flush.fill_(1)
+            events.append(resident_step(b, fb))
+        _lib.tp_conv_hook = None
+        torch.cuda.synchronize()
+        launches = _lib.launch_count - launches0
+        resident_ms = [s.elapsed_time(e) for s, e in events]
+        e2e = [e2e_step(base_seed + 900 + i) for i in range(opts.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tp = timer.summarise()
+    ms_step = float(np.mean(resident_ms))
+    e2e_s = float(np.mean([x[0] for x in e2e]))
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = load_peaks()
+        out = {
+            "metric": "sampled poses/sec", "value": world * SAMPLES / (ms_step * 1e-3), "unit": "poses/s", "n_gpus": world,
+            "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(conf_model is not None),
+            "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": world * SAMPLES / e2e_s, "unit": "poses/s", "h2d_bytes_per_step": int(e2e[0][1]),
+                    "d2h_bytes_per_step": int(e2e[0][2])},
+        }
+        if tp["launches"]:
+            gbs = tp["bytes"] / (tp["ms"] * 1e-3) / 1e9
+            out["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                               "traffic": None, "kernel": "tp_conv_kernel (K3, all launches of the timed region)",
+                               "peak_source": peaks["source"], "launches": tp["launches"],
+                               "avg_launch_ms": tp["ms"] / tp["launches"], "share_of_step": tp["ms"] / (ms_step * opts.steps),
+                               "algorithmic_bytes_per_launch": tp["bytes"] / tp["launches"],
+                               "tflops_reference_formulation": tp["flops_ref"] / (tp["ms"] * 1e-3) / 1e12,
+                               "tflops_executed_fp32": tp["flops_exec"] / (tp["ms"] * 1e-3) / 1e12}
+        if not opts.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(opts)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(opts):
+    """Oracle (reference formulation, CPU, all host threads) on a bounded sample of the same workload."""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-samples", str(opts.ref_samples), "--ref-inf-steps", str(opts.ref_inf_steps)],
+                       capture_output=True, text=True, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+    for line in r.stdout.splitlines()[::-1]:
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    return {"value": None, "unit": "poses/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + r.stderr[-200:]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cb200", choices=["cb200", "reference"])
+    ap.add_argument("--no-confidence", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-samples", type=int, default=2)
+    ap.add_argument("--ref-inf-steps", type=int, default=2)
+    opts = ap.parse_args()
+    if opts.impl == "reference":
+        run_reference(opts)
+    else:
+        opts.warmup = max(opts.warmup, 3)
+        run_cb200(opts)
+
+
+if __name__ == "__main__":
+    main()

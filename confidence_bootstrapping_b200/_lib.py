@@ -198,8 +198,15 @@ def edge_featurize(args: EdgeFeatArgs):
     _launched()
 
 
+tp_conv_hook = None  # optional callable(args) -> context manager; bench.py times K3 launches with CUDA events
+
+
 def tp_conv_forward(args: TpConvArgs):
-    _check(lib().cb_tp_conv_forward(C.byref(args), stream_ptr()), "cb_tp_conv_forward")
+    if tp_conv_hook is not None:
+        with tp_conv_hook(args):
+            _check(lib().cb_tp_conv_forward(C.byref(args), stream_ptr()), "cb_tp_conv_forward")
+    else:
+        _check(lib().cb_tp_conv_forward(C.byref(args), stream_ptr()), "cb_tp_conv_forward")
     _launched()
 
 

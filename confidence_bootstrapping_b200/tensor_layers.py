@@ -204,6 +204,9 @@ class TensorProductConvLayer(nn.Module):
         if residual is not None:
             a.residual, a.d_res, a.ld_res = _lib.f32(residual, "residual"), min(residual.shape[1], P.d_out), residual.shape[1]
         a.out = out.data_ptr()
+        # bookkeeping for profilers (bench.py): which edge counters / sizes this launch covers
+        a._meta = dict(layer=self, n_in=int(x.shape[0]), n_out=int(n_out), groups=groups,
+                       edge_counters=[s.edges.n_edges_dev for s in segments])
         _lib.tp_conv_forward(a)
         return out
 

@@ -113,7 +113,7 @@ def test_edge_featurize(lmax, n_extra, sigma_first, with_sigma):
                    extra=extra.cuda() if n_extra else None)
     ei = edges.edge_index().cpu()
     vec = -(x[ei[1]] - y[ei[0]])
-    smear = torch.exp(sm.coeff * (vec.norm(dim=-1)[:, None] - sm.offset[None, :]) ** 2)
+    smear = torch.exp(sm.coeff * (vec.norm(dim=-1)[:, None] - sm.offset.cpu()[None, :]) ** 2)
     parts = {"extra": extra[:E] if n_extra else torch.zeros(E, 0), "sigma": sigma[by[ei[0]]] if with_sigma else torch.zeros(E, 0),
              "smear": smear}
     feat = torch.cat([parts["extra"], parts["sigma"], parts["smear"]] if sigma_first else [parts["extra"], parts["smear"], parts["sigma"]], 1)
