@@ -284,3 +284,18 @@ def full_tp_1o_block(lmax: int):
         o += 2 * outs[i][0] + 1
     first_1o = next(i for i in range(len(outs)) if outs[i] == (1, -1))
     return o, off[first_1o], w
+
+
+def full_tp_low_blocks(lmax: int):
+    """The l<=1 output blocks of e3nn FullTensorProduct(sh(lmax), '2e') in its sorted output order
+    ((l, p) ascending, odd before even): the only blocks tor_bond_conv can couple to l<=1 node features.
+    Returns (irreps_str, [(l_in, coef[2l_in+1, 5, 2l_out+1])...]) with the sqrt(2 l_out + 1) path weight."""
+    blocks = []
+    for l1 in range(lmax + 1):
+        p1 = (-1) ** l1
+        for lo in range(abs(l1 - 2), l1 + 2 + 1):
+            if lo <= 1:
+                blocks.append((lo, p1, l1))
+    blocks.sort(key=lambda b: (b[0], b[1]))
+    irreps = " + ".join(f"1x{lo}{'e' if p == 1 else 'o'}" for lo, p, _ in blocks)
+    return irreps, [(l1, wigner_3j(l1, 2, lo) * math.sqrt(2 * lo + 1)) for lo, p, l1 in blocks]

@@ -23,7 +23,7 @@ from torch import nn
 
 from . import so3, torus
 from .graph import (EdgeEmbedder, EdgeList, identity_edges, radius_edges, radius_edges_transposed, static_edges)
-from .irreps import full_tp_1o_block, get_irrep_seq, irreps_str, sh_irreps
+from .irreps import full_tp_low_blocks, get_irrep_seq, irreps_str, sh_irreps
 from .synthetic import LIG_FEATURE_DIMS, REC_ATOM_FEATURE_DIMS, REC_RESIDUE_FEATURE_DIMS
 from .tensor_layers import Segment, TensorProductConvLayer
 
@@ -184,20 +184,24 @@ class TensorProductScoreModel(nn.Module):
             self.tr_final_layer = nn.Sequential(nn.Linear(1 + sigma_embed_dim, ns), nn.Dropout(dropout), nn.ReLU(), nn.Linear(ns, 1))
             self.rot_final_layer = nn.Sequential(nn.Linear(1 + sigma_embed_dim, ns), nn.Dropout(dropout), nn.ReLU(), nn.Linear(ns, 1))
             if not no_torsion:
-                self.final_edge_embedding = _edge_mlp(distance_embed_dim, ns, dropout)
-                # o3.FullTensorProduct(sh_irreps, "2e") has no parameters; only its 1o output block can reach
-                # the scalar outputs of tor_bond_conv from l<=1 node features (score_model.py:265-274)
-                if sh_lmax != 1:
-                    raise NotImplementedError("torsion head implemented for sh_lmax=1 (the shipped score model)")
-                _, _, w = full_tp_1o_block(sh_lmax)
-                self.register_buffer("_tor_w121", torch.tensor(w, dtype=torch.float32), persistent=False)
-                self.tor_bond_conv = TensorProductConvLayer(
-                    in_irreps=self.conv_layers[-1].out_irreps, sh_irreps="1x1o", out_irreps=f"{ns}x0o + {ns}x0e",
-                    n_edge_features=3 * ns, residual=False, dropout=dropout, batch_norm=batch_norm)
-                self.tor_final_layer = nn.Sequential(nn.Linear(2 * ns, ns, bias=False), nn.Tanh(), nn.Dropout(dropout),
-                                                     nn.Linear(ns, 1, bias=False))
+                self._init_torsion_head(ns, sh_lmax, dropout, batch_norm, distance_embed_dim)
         # e3nn modules in reference checkpoints carry constant buffers under `*.tp.*` / `final_tp_tor.*`
         self._register_load_state_dict_pre_hook(self._drop_e3nn_buffers)
+
+    def _init_torsion_head(self, ns, sh_lmax, dropout, batch_norm, distance_embed_dim):
+        """final_edge_embedding, final_tp_tor, tor_bond_conv, tor_final_layer (score_model.py:257-280).
+        o3.FullTensorProduct(sh_irreps, "2e") has no parameters; only its l<=1 output blocks can reach the
+        scalar outputs of tor_bond_conv from l<=1 node features, so only those are evaluated."""
+        self.final_edge_embedding = _edge_mlp(distance_embed_dim, ns, dropout)
+        tor_sh_irreps, blocks = full_tp_low_blocks(sh_lmax)
+        self._tor_blocks = [l_in for l_in, _ in blocks]
+        for k, (_, w) in enumerate(blocks):
+            self.register_buffer(f"_tor_w{k}", torch.tensor(w, dtype=torch.float32), persistent=False)
+        self.tor_bond_conv = TensorProductConvLayer(
+            in_irreps=self.conv_layers[-1].out_irreps, sh_irreps=tor_sh_irreps, out_irreps=f"{ns}x0o + {ns}x0e",
+            n_edge_features=3 * ns, residual=False, dropout=dropout, batch_norm=batch_norm)
+        self.tor_final_layer = nn.Sequential(nn.Linear(2 * ns, ns, bias=False), nn.Tanh(), nn.Dropout(dropout),
+                                             nn.Linear(ns, 1, bias=False))
 
     @staticmethod
     def _drop_e3nn_buffers(state_dict, prefix, *args):
@@ -240,7 +244,7 @@ class TensorProductScoreModel(nn.Module):
         nl_h, nr_h = nl.tolist(), nr.tolist()             # one host read per batch (sizes for buffer caps)
         st.nl_h, st.nr_h = nl_h, nr_h
         st.cap_cross = int(sum(a * b for a, b in zip(nl_h, nr_h)))
-        st.cap_lig = int(sum(a * min(a - 1, 32) for a in nl_h if a > 0))
+        st.cap_lig = int(sum(a * min(a - 1, 33) for a in nl_h if a > 0)) + 1
         # static topologies
         st.bond_edges, perm = static_edges(ll.edge_index, st.NL)
         st.bond_attr = ll.edge_attr.float()[perm].contiguous()
@@ -273,6 +277,31 @@ class TensorProductScoreModel(nn.Module):
         rec.cb200_static = {"owner": id(self), "static": st}
         return st
 
+    # ------------------------------------------------------------------ ligand graph + embedding
+    def _ligand_embedding(self, st, lig_pos, sigma_emb, emb):
+        """build_lig_conv_graph + lig_node/edge_embedding + lig_emb_layers (score_model.py:282-295,492-522).
+        Returns (lig_x, lig_segments(group, n1) -> [bond segment, radius segment])."""
+        ns, lmax = self.ns, self.sh_lmax
+        fwd = radius_edges(lig_pos, st.lig_ptr, lig_pos, st.lig_batch, self.lig_max_radius, 33, st.cap_lig,
+                           exclude_self=True)
+        rad = radius_edges_transposed(lig_pos, st.lig_batch, lig_pos, st.lig_ptr, self.lig_max_radius,
+                                      st.cap_lig, exclude_self=True, kept=fwd)
+        bond_attr, bond_sh = emb.lig(st.bond_edges, lig_pos, lig_pos, st.lig_batch, sigma_emb, lmax, extra=st.bond_attr)
+        rad_attr, rad_sh = emb.lig(rad, lig_pos, lig_pos, st.lig_batch, sigma_emb, lmax)
+        lig_x = self.lig_node_embedding.additional_features_embedder(
+            torch.cat([st.lig_cat, sigma_emb[st.lig_batch.long()]], dim=1)).contiguous()
+        NL = st.NL
+
+        def lig_segments(group, n1):
+            return [Segment(st.bond_edges, bond_attr, bond_sh, group, 0, n1),
+                    Segment(rad, rad_attr, rad_sh, group, 0, n1)]
+
+        cols = dict(e_cols=(0, ns), agg_cols=(ns, ns), nbr_cols=(2 * ns, ns))
+        if self.embed_also_ligand:
+            for layer in self.lig_emb_layers:
+                lig_x = layer.run(lig_x, lig_segments(0, NL), NL, ns, residual=lig_x, **cols)
+        return lig_x, lig_segments
+
     # ------------------------------------------------------------------ forward
     def forward(self, data):
         st = self._static(data)
@@ -287,27 +316,9 @@ class TensorProductScoreModel(nn.Module):
         sigma_emb = self.timestep_emb_func(t["tr"]).float().contiguous()             # [B, sigma_embed_dim]
         rec_sigma_emb = self.rec_sigma_embedding(sigma_emb).contiguous()             # [B, ns]
 
-        # ---- ligand graph: bonds (static) + radius graph (score_model.py:492-522)
-        fwd = radius_edges(lig_pos, st.lig_ptr, lig_pos, st.lig_batch, self.lig_max_radius, 33, st.cap_lig + st.NL,
-                           exclude_self=True)
-        rad = radius_edges_transposed(lig_pos, st.lig_batch, lig_pos, st.lig_ptr, self.lig_max_radius,
-                                      st.cap_lig + st.NL, exclude_self=True, kept=fwd)
-        bond_attr, bond_sh = emb.lig(st.bond_edges, lig_pos, lig_pos, st.lig_batch, sigma_emb, lmax, extra=st.bond_attr)
-        rad_attr, rad_sh = emb.lig(rad, lig_pos, lig_pos, st.lig_batch, sigma_emb, lmax)
-        lig_x = self.lig_node_embedding.additional_features_embedder(
-            torch.cat([st.lig_cat, sigma_emb[st.lig_batch.long()]], dim=1)).contiguous()
+        lig_x, lig_segments = self._ligand_embedding(st, lig_pos, sigma_emb, emb)
         NL, NR = st.NL, st.NR
-
-        def lig_segments(group, n1):
-            return [Segment(st.bond_edges, bond_attr, bond_sh, group, 0, n1),
-                    Segment(rad, rad_attr, rad_sh, group, 0, n1)]
-
         cols = dict(e_cols=(0, ns), agg_cols=(ns, ns), nbr_cols=(2 * ns, ns))
-        if self.embed_also_ligand:
-            for layer in self.lig_emb_layers:
-                lig_x = layer.run(lig_x, lig_segments(0, NL), NL, ns, residual=lig_x, **cols)
-        else:
-            assert self.num_prot_emb_layers == 0, "otherwise reimplement padding"
 
         # ---- cross graph (score_model.py:346-351,564-587); both directions are emitted sorted
         if self.dynamic_max_cross:
@@ -346,6 +357,10 @@ class TensorProductScoreModel(nn.Module):
         if self.confidence_mode:
             return self._confidence_head(lig_x, st)
 
+        return self._score_heads(data, st, emb, lig_x, lig_pos, sigma_emb, tr_sigma, rot_sigma, tor_sigma)
+
+    def _score_heads(self, data, st, emb, lig_x, lig_pos, sigma_emb, tr_sigma, rot_sigma, tor_sigma):
+        ns, lmax, dev, B = self.ns, self.sh_lmax, st.dev, st.B
         # ---- translation / rotation head (score_model.py:394-420)
         center = torch.zeros((B, 3), device=dev).index_add_(0, st.lig_batch.long(), lig_pos) * st.inv_nl
         graph_ids = torch.arange(B, dtype=torch.int32, device=dev)
@@ -382,8 +397,10 @@ class TensorProductScoreModel(nn.Module):
         X, Y, Z = u[:, 0], u[:, 1], u[:, 2]
         y2 = math.sqrt(5.0) * torch.stack([s3 * X * Z, s3 * X * Y, Y * Y - 0.5 * (X * X + Z * Z), s3 * Y * Z,
                                            (s3 / 2.0) * (Z * Z - X * X)], -1)
-        # FullTensorProduct(sh, Y2(bond))'s 1o block per edge: sqrt(3) * w3j(1,2,1)[i,j,k] sh1[i] Y2[j]
-        tor_sh = torch.einsum("ijk,ei,ej->ek", self._tor_w121, t_sh[:, 1:4], y2[te.row.long()]).contiguous()
+        # FullTensorProduct(sh, Y2(bond))'s l<=1 blocks per edge: sqrt(2lo+1) * w3j(l,2,lo)[i,j,k] sh_l[i] Y2[j]
+        y2e = y2[te.row.long()]
+        tor_sh = torch.cat([torch.einsum("ijk,ei,ej->ek", getattr(self, f"_tor_w{k}"), t_sh[:, l_in * l_in:(l_in + 1) ** 2], y2e)
+                            for k, l_in in enumerate(self._tor_blocks)], dim=1).contiguous()
         bond_attr_sum = (lig_x[tb[0], :ns] + lig_x[tb[1], :ns]).contiguous()
         seg = [Segment(te, t_attr, tor_sh, 0, 0, n_tor)]
         tor_pred = self.tor_bond_conv.run(lig_x, seg, n_tor, ns, (0, ns), (2 * ns, ns), (ns, ns), agg_scalars=bond_attr_sum)

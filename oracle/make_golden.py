@@ -124,4 +124,32 @@ ga = make_complex(30, 70, 12, all_atoms=True, lm_dim=0)
 gc = copy.deepcopy(ga)
 crop_beyond(gc, 12.0, True)
 save("crop.pt", {"graph": pack_graph(ga), "cutoff": 12.0, "cropped": pack_graph(gc)})
+# 6. small all-atom confidence model: forward, and sampling + crop_beyond + confidence scoring -------------
+from confidence_bootstrapping_b200.configs import confidence_model_args  # noqa: E402
+cargs = confidence_model_args(ns=8, nv=2, num_conv_layers=3, esm_embeddings_path=None, crop_beyond=12.0)
+torch.manual_seed(13)
+cmodel = get_model(cargs, dev, t_to_sigma=None, no_parallel=True, confidence_mode=True)
+randomize_norm_stats(cmodel, seed=4)
+cmodel.eval()
+agraphs = [make_complex(40, 50, 10, all_atoms=True, lm_dim=0), make_complex(41, 44, 15, all_atoms=True, lm_dim=0)]
+cb = Batch.from_data_list(copy.deepcopy(agraphs))
+set_time(cb, 0, 0, 0, 0, 2, True, False, dev)
+with torch.no_grad():
+    conf, atom_conf = cmodel(cb)
+g1 = Batch.from_data_list([copy.deepcopy(agraphs[1])])
+np.random.seed(3)
+torch.manual_seed(3)
+data_list = [copy.deepcopy(g1) for _ in range(4)]
+randomize_position(data_list, args.no_torsion, False, 3.0)     # small spread so that cropping keeps residues
+start = torch.stack([d["ligand"].pos.clone() for d in data_list])
+filt = copy.deepcopy(data_list)
+with injected_noise(seed=6):
+    out, sconf = sampling(data_list=data_list, model=model, inference_steps=3, tr_schedule=sched[:3] * 0.2, rot_schedule=sched[:3] * 0.2,
+                          tor_schedule=sched[:3] * 0.2, device=dev, t_to_sigma=t_to_sigma, model_args=args, batch_size=2,
+                          confidence_model=cmodel, filtering_data_list=filt, filtering_model_args=cargs)
+save("confidence_small.pt", {"args": vars(cargs), "state_dict": {k: v.clone() for k, v in cmodel.state_dict().items()},
+                             "graphs": [pack_graph(x) for x in agraphs], "confidence": conf, "atom_confidence": atom_conf,
+                             # the score model of this run is the one stored in score_small.pt
+                             "sample_start": start, "sample_sched": torch.tensor(sched[:3] * 0.2), "sample_noise_seed": 6,
+                             "sample_final": torch.stack([d["ligand"].pos for d in out]), "sample_confidence": sconf})
 print("done")

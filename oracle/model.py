@@ -293,7 +293,17 @@ def cg_forward(sd, hp, data, t_to_sigma, so3_score_norm, torus_score_norm):
 
     if hp.confidence_mode:
         return _confidence_head(sd, hp, lig_x, lig.batch, B)
+    return _score_heads(sd, hp, data, lig_x, node_sigma, out_irreps, emb_t, tr_sigma, rot_sigma, tor_sigma,
+                        so3_score_norm, torus_score_norm)
 
+
+def _score_heads(sd, hp, data, lig_x, node_sigma, out_irreps, emb_t, tr_sigma, rot_sigma, tor_sigma,
+                 so3_score_norm, torus_score_norm):
+    """Translation / rotation / torsion heads shared by the CG and all-atom score models
+    (score_model.py:394-449 == all_atom_score_model.py:457-507)."""
+    ns, lmax = hp.ns, hp.sh_lmax
+    lig, ll = data["ligand"], data["ligand", "ligand"]
+    B, ct = data.num_graphs, data.complex_t
     # translation / rotation head (:394-420)
     cidx = torch.stack([lig.batch, torch.arange(len(lig.batch))])
     center = torch.zeros((B, 3)).index_add_(0, lig.batch, lig.pos) / torch.bincount(lig.batch, minlength=B).unsqueeze(1)
@@ -366,3 +376,124 @@ def _confidence_head(sd, hp, lig_x, lig_batch, B):
         atom_conf = torch.zeros((len(lig_x),))
     conf = _conf_mlp(sd, "confidence_predictor", scatter_mean(s, lig_batch, dim=0, dim_size=B)).squeeze(dim=-1)
     return conf, atom_conf
+
+
+# ----------------------------------------------------------------------------- all-atom model
+def aa_forward(sd, hp, data, t_to_sigma, so3_score_norm, torus_score_norm):
+    """models/all_atom_score_model.py:363-507 (eval mode; the shipped confidence model is this in confidence mode)."""
+    ns, lmax = hp.ns, hp.sh_lmax
+    lig, rec, atom = data["ligand"], data["receptor"], data["atom"]
+    rr, aa, ar = data["receptor", "receptor"], data["atom", "atom"], data["atom", "receptor"]
+    B, ct = data.num_graphs, data.complex_t
+    if not hp.confidence_mode:
+        tr_sigma, rot_sigma, tor_sigma = t_to_sigma(ct["tr"], ct["rot"], ct["tor"])
+    else:
+        tr_sigma, rot_sigma, tor_sigma = ct["tr"], ct["rot"], ct["tor"]
+    emb_t = lambda t: sinusoidal(t, hp.sigma_embed_dim, hp.embedding_scale)
+    seq = irrep_seq(hp.ns, hp.nv, hp.reduce_pseudoscalars)
+
+    # receptor / atom embedding (:274-329)
+    rei, aei, arei = rr.edge_index.long(), aa.edge_index.long(), ar.edge_index.long()
+    rvec = rec.pos[rei[1]] - rec.pos[rei[0]]
+    rec_ea = _fc(sd, "rec_edge_embedding", _smear(sd, "rec_distance_expansion", rvec.norm(dim=-1)))
+    rec_sh = _sh(lmax, rvec)
+    avec = atom.pos[aei[1]] - atom.pos[aei[0]]
+    atom_ea = _fc(sd, "atom_edge_embedding", _smear(sd, "lig_distance_expansion", avec.norm(dim=-1)))
+    atom_sh = _sh(lmax, avec)
+    arvec = rec.pos[arei[1]] - atom.pos[arei[0]]
+    ar_ea = _fc(sd, "ar_edge_embedding", _smear(sd, "rec_distance_expansion", arvec.norm(dim=-1)))
+    ar_sh = _sh(lmax, arvec)
+    rec_x = _atom_encoder(sd, "rec_node_embedding", rec.x, 1)
+    atom_x = _atom_encoder(sd, "atom_node_embedding", atom.x, 4)
+    nr = len(rec_x)
+    if hp.num_prot_emb_layers > 0:
+        x = torch.cat([rec_x, atom_x], dim=0)
+        are = arei.clone()
+        are[0] = are[0] + nr
+        ei = torch.cat([rei, are, aei + nr, torch.flip(are, dims=[0])], dim=1)
+        ea_all = torch.cat([rec_ea, ar_ea, atom_ea, ar_ea], dim=0)
+        sh_all = torch.cat([rec_sh, ar_sh, atom_sh, ar_sh], dim=0)
+        s1, s2, s3 = rei.shape[1], rei.shape[1] + are.shape[1], rei.shape[1] + are.shape[1] + aei.shape[1]
+        for l in range(hp.num_prot_emb_layers):
+            ea = torch.cat([ea_all, x[ei[0], :ns], x[ei[1], :ns]], -1)
+            groups = 4 if hp.differentiate_convolutions else 1
+            if groups > 1:
+                ea = [ea[:s1], ea[s1:s2], ea[s2:s3], ea[s3:]]
+            x = tp_conv_layer(sd, f"rec_emb_layers.{l}", node_attr=x, edge_index=ei, edge_attr=ea, edge_sh=sh_all,
+                              **_conv_args(hp, l, groups))
+        rec_x, atom_x = x[:nr], x[nr:]
+    rec_sigma = _fc(sd, "rec_sigma_embedding", emb_t(ct["tr"]))
+    rec_x, atom_x = rec_x + 0, atom_x + 0
+    rec_x[:, :ns] = rec_x[:, :ns] + rec_sigma[rec.batch]
+    atom_x[:, :ns] = atom_x[:, :ns] + rec_sigma[atom.batch]
+    rec_ea = rec_ea + rec_sigma[rec.batch[rei[0]]]
+    atom_ea = atom_ea + rec_sigma[atom.batch[aei[0]]]
+    ar_ea = ar_ea + rec_sigma[atom.batch[arei[0]]]
+
+    # ligand (:345-356)
+    node_sigma = emb_t(lig.node_t["tr"]) if "node_t" in lig else emb_t(ct["tr"])[lig.batch]
+    lig_in, lei, lea, lsh = _lig_graph(sd, hp, data, node_sigma)
+    lig_x = _atom_encoder(sd, "lig_node_embedding", lig_in, len(LIG_FEATURE_DIMS))
+    lig_ea = _fc(sd, "lig_edge_embedding", lea)
+    if hp.embed_also_ligand:
+        for l in range(hp.num_prot_emb_layers):
+            ea = torch.cat([lig_ea, lig_x[lei[0], :ns], lig_x[lei[1], :ns]], -1)
+            lig_x = tp_conv_layer(sd, f"lig_emb_layers.{l}", node_attr=lig_x, edge_index=lei, edge_attr=ea, edge_sh=lsh,
+                                  **_conv_args(hp, l, 1))
+    else:
+        lig_x = F.pad(lig_x, (0, rec_x.shape[-1] - lig_x.shape[-1]))
+
+    # cross graphs (:587-622)
+    if hp.dynamic_max_cross:
+        cut = (tr_sigma * 3 + 20).unsqueeze(1)
+        lrei = radius(rec.pos / cut[rec.batch], lig.pos / cut[lig.batch], 1, rec.batch, lig.batch, max_num_neighbors=10000)
+    else:
+        lrei = radius(rec.pos, lig.pos, hp.cross_max_distance, rec.batch, lig.batch, max_num_neighbors=10000)
+    lrvec = rec.pos[lrei[1]] - lig.pos[lrei[0]]
+    lr_ea = _fc(sd, "lr_edge_embedding", torch.cat([node_sigma[lrei[0]], _smear(sd, "cross_distance_expansion", lrvec.norm(dim=-1))], 1))
+    lr_sh = _sh(lmax, lrvec)
+    laei = radius(atom.pos, lig.pos, hp.lig_max_radius, atom.batch, lig.batch, max_num_neighbors=10000)
+    lavec = atom.pos[laei[1]] - lig.pos[laei[0]]
+    la_ea = _fc(sd, "la_edge_embedding", torch.cat([node_sigma[laei[0]], _smear(sd, "lig_distance_expansion", lavec.norm(dim=-1))], 1))
+    la_sh = _sh(lmax, lavec)
+
+    # joint graph: nodes [lig ; rec ; atom], nine edge groups (:396-418)
+    nl = len(lig_x)
+    x = torch.cat([lig_x, rec_x, atom_x], dim=0)
+    rei2, aei2 = rei + nl, aei + nl + nr
+    lrei2, laei2, arei2 = lrei.clone(), laei.clone(), arei.clone()
+    lrei2[1] += nl
+    laei2[1] += nl + nr
+    arei2[0] += nl + nr
+    arei2[1] += nl
+    parts = [(lei, lig_ea, lsh), (lrei2, lr_ea, lr_sh), (laei2, la_ea, la_sh), (rei2, rec_ea, rec_sh),
+             (torch.flip(lrei2, dims=[0]), lr_ea, lr_sh), (torch.flip(arei2, dims=[0]), ar_ea, ar_sh),
+             (aei2, atom_ea, atom_sh), (torch.flip(laei2, dims=[0]), la_ea, la_sh), (arei2, ar_ea, ar_sh)]
+    ei = torch.cat([p[0] for p in parts], dim=1)
+    ea_all = torch.cat([p[1] for p in parts], dim=0)
+    sh_all = torch.cat([p[2] for p in parts], dim=0)
+    cuts = np.cumsum([p[0].shape[1] for p in parts]).tolist()
+    n_conv = hp.num_conv_layers
+    for l in range(n_conv):
+        idx = hp.num_prot_emb_layers + l
+        if l < n_conv - 1:
+            ea = torch.cat([ea_all, x[ei[0], :ns], x[ei[1], :ns]], -1)
+            groups = 9 if hp.differentiate_convolutions else 1
+            if groups > 1:
+                ea = [ea[a:b] for a, b in zip([0] + cuts[:-1], cuts)]
+            x = tp_conv_layer(sd, f"conv_layers.{l}", node_attr=x, edge_index=ei, edge_attr=ea, edge_sh=sh_all,
+                              **_conv_args(hp, idx, groups))
+        else:
+            s3 = cuts[2]
+            ea = torch.cat([ea_all[:s3], x[ei[0, :s3], :ns], x[ei[1, :s3], :ns]], -1)
+            groups = 3 if hp.differentiate_convolutions else 1
+            if groups > 1:
+                ea = [ea[:cuts[0]], ea[cuts[0]:cuts[1]], ea[cuts[1]:s3]]
+            x = tp_conv_layer(sd, f"conv_layers.{l}", node_attr=x, edge_index=ei[:, :s3], edge_attr=ea, edge_sh=sh_all[:s3],
+                              **_conv_args(hp, idx, groups))
+    lig_x = x[:nl]
+    if hp.confidence_mode:
+        return _confidence_head(sd, hp, lig_x, lig.batch, B)
+    out_irreps = seq[min(hp.num_prot_emb_layers + n_conv, 3)]
+    return _score_heads(sd, hp, data, lig_x, node_sigma, out_irreps, emb_t, tr_sigma, rot_sigma, tor_sigma,
+                        so3_score_norm, torus_score_norm)

@@ -117,3 +117,34 @@ def test_crop_beyond_restatement():
     for et in (("receptor", "receptor"), ("atom", "atom"), ("atom", "receptor")):
         assert torch.equal(graph[et].edge_index, want[et].edge_index)
     assert 0 < graph["receptor"].pos.shape[0] < unpack_graph(g["graph"])["receptor"].pos.shape[0]
+
+
+def test_confidence_model_and_filtered_sampling_restatement():
+    """All-atom confidence model forward, and sampling -> crop_beyond -> confidence scoring, against the real
+    reference's outputs (confidences within 1e-4, BASELINE.json)."""
+    g = load("confidence_small.pt")
+    gs, sargs, t2s, score_fwd = _small_model_inputs()
+    cargs = Namespace(**g["args"])
+    hp = om.hyper_from_args(cargs, confidence_mode=True)
+    conf_fwd = lambda b: om.aa_forward(g["state_dict"], hp, b, None, pso3.score_norm, ptorus.score_norm)
+    batch = Batch.from_data_list([unpack_graph(x) for x in g["graphs"]])
+    osamp.set_time(batch, 0, 0, 0, 2, all_atoms=True)
+    with torch.no_grad():
+        conf, atom_conf = conf_fwd(batch)
+    assert torch.allclose(conf, g["confidence"], atol=1e-5) and torch.allclose(atom_conf, g["atom_confidence"], atol=1e-5)
+    base = Batch.from_data_list([unpack_graph(g["graphs"][1])])
+    data_list = []
+    for s in g["sample_start"]:
+        d = copy.deepcopy(base)
+        d["ligand"].pos = s.clone()
+        data_list.append(d)
+    filt = copy.deepcopy(data_list)
+    sched = g["sample_sched"].numpy()
+    with injected_noise(seed=g["sample_noise_seed"]):
+        out, sconf = osamp.sampling(data_list, score_fwd, 3, sched, sched, sched, t2s, sargs, batch_size=2,
+                                    confidence_forward=conf_fwd, filtering_data_list=filt, filtering_model_args=cargs,
+                                    crop_fn=osamp.crop_beyond)
+    for d, want in zip(out, g["sample_final"]):
+        assert rmsd(d["ligand"].pos, want) < 1e-3
+    assert sconf.shape == g["sample_confidence"].shape
+    assert torch.allclose(sconf, g["sample_confidence"], atol=1e-4)

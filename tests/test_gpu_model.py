@@ -133,3 +133,108 @@ def test_model_refuses_training_mode():
     set_time(b, None, 0.5, 0.5, 0.5, 1, False, False, torch.device("cuda"))
     with pytest.raises(NotImplementedError):
         model(b)
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def test_crop_beyond_bit_exact():
+    """Device crop (K1 mask + prefix-sum compaction) vs the reference's host crop: identical tensors/indices,
+    single graph (golden from the real utils/utils.py:395-420) and a batch of heterogeneous graphs (oracle)."""
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    from confidence_bootstrapping_b200.utils import crop_beyond
+    g = _load("crop.pt")
+    got = crop_beyond(Batch.from_data_list([unpack_graph(g["graph"])]).to("cuda"), g["cutoff"], True)
+    want = unpack_graph(g["cropped"])
+    for nt in ("receptor", "atom"):
+        assert torch.equal(got[nt].pos.cpu(), want[nt].pos) and torch.equal(got[nt].x.cpu(), want[nt].x)
+    for et in (("receptor", "receptor"), ("atom", "atom"), ("atom", "receptor")):
+        assert torch.equal(got[et].edge_index.cpu(), want[et].edge_index)
+    graphs = [make_complex(60 + i, 40 + 9 * i, 8 + 2 * i, all_atoms=True, lm_dim=3) for i in range(3)]
+    cropped = [osamp.crop_beyond(copy.deepcopy(x), 10.0, True) for x in graphs]
+    want_b = Batch.from_data_list(cropped)
+    got_b = crop_beyond(Batch.from_data_list(copy.deepcopy(graphs)).to("cuda"), 10.0, True)
+    for nt in ("receptor", "atom"):
+        assert torch.equal(got_b[nt].pos.cpu(), want_b[nt].pos) and torch.equal(got_b[nt].batch.cpu(), want_b[nt].batch)
+    for et in (("receptor", "receptor"), ("atom", "atom"), ("atom", "receptor")):
+        assert torch.equal(got_b[et].edge_index.cpu(), want_b[et].edge_index)
+
+
+def test_golden_confidence_model_and_filtered_sampling():
+    """Reference-produced golden: all-atom confidence model (lmax 2, 9 edge groups) forward, and
+    sampling -> crop_beyond -> confidence scoring.  Confidences within 1e-4, poses within 1e-3 A."""
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import set_time, t_to_sigma as t2s_full
+    from confidence_bootstrapping_b200.sampling import sampling
+    from confidence_bootstrapping_b200.utils import get_model
+    g, gs = _load("confidence_small.pt"), _load("score_small.pt")
+    dev = torch.device("cuda")
+    cargs, sargs = Namespace(**g["args"]), Namespace(**gs["args"])
+    t2s = partial(t2s_full, args=sargs)
+    cmodel = get_model(cargs, dev, t_to_sigma=None, no_parallel=True, confidence_mode=True)
+    cmodel.load_state_dict(g["state_dict"], strict=True)
+    cmodel.eval()
+    smodel = get_model(sargs, dev, t_to_sigma=t2s, no_parallel=True)
+    smodel.load_state_dict(gs["state_dict"], strict=True)
+    smodel.eval()
+    batch = Batch.from_data_list([unpack_graph(x) for x in g["graphs"]]).to(dev)
+    set_time(batch, 0, 0, 0, 0, 2, True, False, dev)
+    with torch.no_grad():
+        conf, atom_conf = cmodel(batch)
+    assert torch.allclose(conf.cpu(), g["confidence"], atol=1e-4) and torch.allclose(atom_conf.cpu(), g["atom_confidence"], atol=1e-4)
+    base = Batch.from_data_list([unpack_graph(g["graphs"][1])])
+    data_list = []
+    for s in g["sample_start"]:
+        d = copy.deepcopy(base)
+        d["ligand"].pos = s.clone()
+        data_list.append(d)
+    filt = copy.deepcopy(data_list)
+    sched = g["sample_sched"].numpy()
+    with injected_noise(seed=g["sample_noise_seed"]):
+        out, sconf = sampling(data_list=data_list, model=smodel, inference_steps=3, tr_schedule=sched, rot_schedule=sched,
+                              tor_schedule=sched, device=dev, t_to_sigma=t2s, model_args=sargs, batch_size=2,
+                              confidence_model=cmodel, filtering_data_list=filt, filtering_model_args=cargs)
+    for d, want in zip(out, g["sample_final"]):
+        assert rmsd(d["ligand"].pos, want) < 1e-3
+    assert torch.allclose(sconf.cpu(), g["sample_confidence"], atol=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["confidence", "score_lmax2"])
+def test_all_atom_model_vs_oracle(mode):
+    """Shipped confidence hyper-parameters (ns 24, nv 6, 5 layers, lmax 2, 9 groups, 1280-d LM), and an all-atom
+    SCORE model with lmax 2 (torsion head through the l<=1 blocks of FullTensorProduct(sh, 2e))."""
+    from confidence_bootstrapping_b200 import so3, torus
+    from confidence_bootstrapping_b200.configs import confidence_model_args, score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import set_time, t_to_sigma as t2s_full
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    from confidence_bootstrapping_b200.utils import get_model
+    dev = torch.device("cuda")
+    if mode == "confidence":
+        args, cm, t = confidence_model_args(), True, 0.0
+    else:
+        args, cm, t = score_model_args(all_atoms=True, sh_lmax=2, ns=24, nv=6, num_conv_layers=3, num_prot_emb_layers=1), False, 0.5
+    t2s = partial(t2s_full, args=args) if not cm else None
+    torch.manual_seed(5)
+    model = get_model(args, dev, t_to_sigma=t2s, no_parallel=True, confidence_mode=cm)
+    randomize_norm_stats(model, seed=6)
+    model.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    hp = om.hyper_from_args(args, confidence_mode=cm)
+    graphs = [make_complex(90 + i, 50 + 20 * i, 11 + 4 * i, all_atoms=True) for i in range(2)]
+    cpu = Batch.from_data_list(copy.deepcopy(graphs))
+    osamp.set_time(cpu, t, t, t, 2, all_atoms=True)
+    gpu = Batch.from_data_list(copy.deepcopy(graphs)).to(dev)
+    set_time(gpu, None, t, t, t, 2, True, False, dev)
+    with torch.no_grad():
+        want = om.aa_forward(sd, hp, cpu, partial(osamp.t_to_sigma, args=args) if not cm else None, so3.score_norm, torus.score_norm)
+        got = model(gpu)
+    n = 2 if cm else 3
+    for a, b in zip(got[:n], want[:n]):
+        assert a.shape == b.shape
+        if cm:
+            assert torch.allclose(a.cpu(), b, atol=1e-4)      # confidences within 1e-4 (BASELINE.json)
+        else:
+            assert rel_err(a, b) < 1e-4
