@@ -39,7 +39,7 @@ class TpSegment(C.Structure):
         ("ldp_agg", C.c_int32), ("ldp_nbr", C.c_int32),
         ("W1e", C.c_void_p), ("ldw1", C.c_int32),
         ("b1", C.c_void_p), ("W2", C.c_void_p), ("b2", C.c_void_p),
-        ("n0", C.c_int32), ("n1", C.c_int32), ("col_off", C.c_int32), ("pad_", C.c_int32),
+        ("n0", C.c_int32), ("n1", C.c_int32), ("col_off", C.c_int32), ("slot", C.c_int32),
     ]
 
 
@@ -51,10 +51,11 @@ class TpConvArgs(C.Structure):
         ("x", C.c_void_p), ("d_in", C.c_int32), ("d_out", C.c_int32), ("S", C.c_int32), ("ne", C.c_int32),
         ("H", C.c_int32), ("n_out", C.c_int32), ("agg_graph", C.c_void_p),
         ("rows", C.c_void_p), ("n_rows", C.c_int32), ("terms", C.c_void_p), ("n_terms", C.c_int32),
-        ("out_ptr", C.c_void_p), ("out_idx", C.c_void_p), ("n_slots", C.c_int32), ("n_segs", C.c_int32),
+        ("runs", C.c_void_p), ("n_runs", C.c_int32), ("n_segs", C.c_int32),
         ("segs", TpSegment * CB_MAX_SEGS),
         ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p), ("residual", C.c_void_p),
         ("d_res", C.c_int32), ("ld_res", C.c_int32), ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_floats", C.c_int64), ("node_begin", C.c_int32), ("node_end", C.c_int32),
     ]
 
 
@@ -71,7 +72,7 @@ class SdeStepArgs(C.Structure):
 
 EXPORTS = [
     "cb_last_error", "cb_version", "cb_sizeof", "cb_radius_count", "cb_radius_fill", "cb_radius_count_t", "cb_radius_fill_t",
-    "cb_exclusive_scan_i32", "cb_edge_featurize", "cb_tp_conv_forward", "cb_sde_step",
+    "cb_exclusive_scan_i32", "cb_edge_featurize", "cb_tp_conv_forward", "cb_tp_conv_items", "cb_sde_step",
 ]
 
 _lib = None
@@ -94,6 +95,7 @@ def lib():
         l.cb_last_error.restype = C.c_char_p
         for name in EXPORTS[1:]:
             getattr(l, name).restype = C.c_int
+        l.cb_tp_conv_items.restype = C.c_int64
         _lib = l
     return _lib
 
@@ -201,13 +203,17 @@ def edge_featurize(args: EdgeFeatArgs):
 tp_conv_hook = None  # optional callable(args) -> context manager; bench.py times K3 launches with CUDA events
 
 
+def tp_conv_items(args: TpConvArgs) -> int:
+    return int(lib().cb_tp_conv_items(C.byref(args)))
+
+
 def tp_conv_forward(args: TpConvArgs):
     if tp_conv_hook is not None:
         with tp_conv_hook(args):
             _check(lib().cb_tp_conv_forward(C.byref(args), stream_ptr()), "cb_tp_conv_forward")
     else:
         _check(lib().cb_tp_conv_forward(C.byref(args), stream_ptr()), "cb_tp_conv_forward")
-    _launched()
+    _launched(2)
 
 
 def sde_step(args: SdeStepArgs):

@@ -24,6 +24,7 @@ extern "C" int cb_sizeof(int which) {
         case 3: return (int)sizeof(cb_sde_step_args);
         case 4: return (int)sizeof(cb_tp_row);
         case 5: return (int)sizeof(cb_tp_term);
+        case 6: return (int)sizeof(cb_tp_run);
         default: return -1;
     }
 }

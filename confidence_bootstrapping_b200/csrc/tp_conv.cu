@@ -2,28 +2,59 @@
 // Replaces TensorProductConvLayer.forward (models/tensor_layers.py:195-217): gather, radial MLP,
 // FasterTensorProduct / e3nn FullyConnectedTensorProduct, scatter-mean, BatchNorm(eval), residual.
 //
-// Formulation (exact up to fp re-association).  For aggregation node i and edge segment s
-//     sum_{e in s, e->i} tp_e  =  T_s( A ),   A[r][j] = sum_e f_e[r] * h~_e[j]
+// Formulation (exact up to fp re-association).  For aggregation node i and slot q (= edge group)
+//     sum_{e in q, e->i} tp_e  =  T_q( A ),   A[r][j] = sum_e f_e[r] * h~_e[j]
 //   f_e[r]  : the CG "intermediates" of the tensor product, sum of coef * x[col[e]][.] * sh_e[.]
 //             (R rows; FasterTensorProduct's out_dict entries tensor_layers.py:72-85, or one row
 //             per (e3nn instruction, u, k))
 //   h~_e    : [relu(W1 a_e + b1) ; 1]  (H+1 columns), the hidden layer of the radial MLP (layers.py:8-15)
-//   T_s(A)[o(r,m)] += sum_j W2[w(r)+m][j] A[r][j] + b2[w(r)+m] A[r][H]
-// so the [E, weight_numel] per-edge weight tensor of the reference (6.6 KB per edge) is never
-// formed: per edge the kernel does an R x H rank-1 update held in registers (one CTA per node,
-// NRT x NCT threads each owning a TR x TC tile of A), and the weight_numel x H contraction with W2
-// happens once per (node, segment) instead of once per edge.
+//   T_q(A)[o(r,m)] += sum_j W2[w(r)+m][j] A[r][j] + b2[w(r)+m] A[r][H]
+// so the [E, weight_numel] per-edge weight tensor of the reference (6.6 KB per edge) is never formed.
 //
-// One CTA per aggregation node; heavy nodes (ligand atoms with hundreds of cross edges) come first in
-// the node ordering so the tail of the grid is made of light receptor nodes.  Everything is
-// deterministic: segmented in-register / shuffle / fixed-order shared-memory reductions, no atomics.
+// Two kernels:
+//  (a) tp_accumulate_kernel  one CTA per (node, slot): R x H rank-1 updates per edge held in registers
+//      (NRT x NCT threads, each a TR x TC tile), the finished tile written once to the workspace
+//      (R x (H+4) floats per (node, slot); column H carries sum_e f_e for the bias term).
+//  (b) tp_transform_kernel   one CTA per 32 nodes: for every slot and every run of rows it streams the
+//      W2 rows once per 32 nodes through shared memory (the v1 single-kernel design re-read all of W2
+//      per node and serialised the contraction on the 3 warps owning the 0e rows: profiles/r1),
+//      then mean over all incoming edges, BatchNorm(eval) affine, residual.
+// Everything is deterministic: fixed-order register / shared-memory reductions, no atomics.
 #include "common.cuh"
 #include "../../include/cb200.h"
 
 namespace {
 
-constexpr int CH = 16;  // edges staged per chunk
+constexpr int CH = 32;   // edges staged per chunk in the accumulate kernel
+constexpr int PADC = 4;  // extra workspace columns per row: [H] = sum_e f_e, [H+1..H+3] = 0
 
+struct SlotTable {
+    int n_slots;
+    int first_seg[CB_MAX_SEGS], n_segs[CB_MAX_SEGS];
+    int lo[CB_MAX_SEGS], hi[CB_MAX_SEGS];   // node range of the slot clipped to [node_begin, node_end)
+    int item_off[CB_MAX_SEGS + 1];
+};
+
+__host__ __device__ inline void build_slots(const cb_tp_conv_args& a, SlotTable& t) {
+    t.n_slots = 0;
+    t.item_off[0] = 0;
+    for (int s = 0; s < a.n_segs; ++s) {
+        if (s > 0 && a.segs[s].slot == a.segs[s - 1].slot) {
+            t.n_segs[t.n_slots - 1]++;
+            continue;
+        }
+        const int q = t.n_slots++;
+        t.first_seg[q] = s;
+        t.n_segs[q] = 1;
+        const int lo = a.segs[s].n0 > a.node_begin ? a.segs[s].n0 : a.node_begin;
+        const int hi = a.segs[s].n1 < a.node_end ? a.segs[s].n1 : a.node_end;
+        t.lo[q] = lo;
+        t.hi[q] = hi > lo ? hi : lo;
+        t.item_off[q + 1] = t.item_off[q] + (t.hi[q] - t.lo[q]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ (a)
 template <int NRT_, int NCT_, int TR_, int TC_>
 struct Cfg {
     static constexpr int NRT = NRT_, NCT = NCT_, TR = TR_, TC = TC_;
@@ -31,12 +62,11 @@ struct Cfg {
 };
 
 struct SmemLayout {
-    int rows, terms, w1e, hbase, cols, xs, shs, es, F, Hs, P, outacc, total;  // offsets in 4-byte words
+    int rows, terms, w1e, hbase, cols, xs, shs, es, F, Hs, total;  // offsets in 4-byte words
     int nep, dxp;
 };
 
-__host__ __device__ inline SmemLayout make_layout(int n_rows, int n_terms, int ne, int d_in, int S, int n_slots,
-                                                  int d_out, int RP, int HP) {
+__host__ __device__ inline SmemLayout make_layout(int n_rows, int n_terms, int ne, int d_in, int S, int RP, int HP) {
     SmemLayout L;
     auto al4 = [](int v) { return (v + 3) & ~3; };
     int o = 0;
@@ -52,19 +82,17 @@ __host__ __device__ inline SmemLayout make_layout(int n_rows, int n_terms, int n
     L.es = o;     o += al4(CH * ne);
     L.F = o;      o += al4(CH * RP);
     L.Hs = o;     o += al4(CH * HP);
-    L.P = o;      o += al4(n_slots);
-    L.outacc = o; o += al4(d_out);
     L.total = o;
     return L;
 }
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
-tp_conv_kernel(const __grid_constant__ cb_tp_conv_args a) {
+tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a) {
     constexpr int NCT = C::NCT, TR = C::TR, TC = C::TC, RP = C::RP, HP = C::HP, THREADS = C::THREADS;
     static_assert(TR == 4 && TC % 4 == 0, "tile shape");
     extern __shared__ __align__(16) float sm[];
-    const SmemLayout L = make_layout(a.n_rows, a.n_terms, a.ne, a.d_in, a.S, a.n_slots, a.d_out, RP, HP);
+    const SmemLayout L = make_layout(a.n_rows, a.n_terms, a.ne, a.d_in, a.S, RP, HP);
     cb_tp_row* rows_s = reinterpret_cast<cb_tp_row*>(sm + L.rows);
     cb_tp_term* terms_s = reinterpret_cast<cb_tp_term*>(sm + L.terms);
     float* W1e_s = sm + L.w1e;
@@ -75,15 +103,30 @@ tp_conv_kernel(const __grid_constant__ cb_tp_conv_args a) {
     float* es = sm + L.es;
     float* F = sm + L.F;
     float* Hs = sm + L.Hs;
-    float* P = sm + L.P;
-    float* outacc = sm + L.outacc;
+    __shared__ SlotTable st;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int tr = tid / NCT, tc = tid % NCT;
-    const int node = blockIdx.x;
     const int H = a.H, ne = a.ne, S = a.S, d_in = a.d_in, n_rows = a.n_rows, nep = L.nep, dxp = L.dxp;
+    const int HA = H + PADC;
 
-    // one-time staging: TP program, zeroed tiles
+    if (tid == 0) build_slots(a, st);
+    __syncthreads();
+    // item -> (slot, node)
+    int q = 0;
+    const int item = blockIdx.x;
+    while (q + 1 < st.n_slots && item >= st.item_off[q + 1]) ++q;
+    const int node = st.lo[q] + (item - st.item_off[q]);
+    const int seg0 = st.first_seg[q], nseg = st.n_segs[q];
+    int deg = 0;
+    for (int s = seg0; s < seg0 + nseg; ++s) {
+        const cb_tp_segment& sg = a.segs[s];
+        deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
+    }
+    if (deg == 0) return;  // block-uniform; the transform kernel skips (node, slot) pairs without edges
+
+    // one-time staging: TP program, zeroed tiles, slot-level MLP pieces
+    const cb_tp_segment& s0 = a.segs[seg0];
     {
         const int* src = reinterpret_cast<const int*>(a.rows);
         int* dst = reinterpret_cast<int*>(rows_s);
@@ -93,55 +136,46 @@ tp_conv_kernel(const __grid_constant__ cb_tp_conv_args a) {
         for (int i = tid; i < a.n_terms; i += THREADS) tdst[i] = tsrc[i];
         for (int i = tid; i < CH * RP; i += THREADS) F[i] = 0.0f;
         for (int i = tid; i < CH * HP; i += THREADS) Hs[i] = 0.0f;
-        for (int i = tid; i < a.d_out; i += THREADS) outacc[i] = 0.0f;
+        for (int i = tid; i < HP * ne; i += THREADS) {
+            const int qq = i / ne, c = i - qq * ne;
+            W1e_s[qq * nep + c] = qq < H ? s0.W1e[(size_t)qq * s0.ldw1 + c] : 0.0f;
+        }
     }
     const int graph = a.agg_graph ? a.agg_graph[node] : 0;
-    int deg_total = 0;
     __syncthreads();
-
-    for (int s = 0; s < a.n_segs; ++s) {
-        const cb_tp_segment& sg = a.segs[s];
-        if (node < sg.n0 || node >= sg.n1) continue;  // block-uniform
-        const int e0 = sg.rowptr[node - sg.n0], e1 = sg.rowptr[node - sg.n0 + 1];
-        if (e1 <= e0) continue;
-        deg_total += e1 - e0;
-
-        // ---- per-segment setup: edge-embedding slice of the first Linear, constant part of h
-        for (int i = tid; i < HP * ne; i += THREADS) {
-            const int q = i / ne, c = i - q * ne;
-            W1e_s[q * nep + c] = q < H ? sg.W1e[(size_t)q * sg.ldw1 + c] : 0.0f;
-        }
-        __syncthreads();
-        for (int q = tid; q < HP; q += THREADS) {
-            float v = 0.0f;
-            if (q < H) {
-                v = sg.b1[q];
-                if (sg.P_agg) v += sg.P_agg[(size_t)node * sg.ldp_agg + q];
-                if (sg.e_post) {
-                    const float* ep = sg.e_post + (size_t)graph * ne;
-                    for (int c = 0; c < ne; ++c) v = fmaf(W1e_s[q * nep + c], ep[c], v);
-                }
+    for (int qq = tid; qq < HP; qq += THREADS) {
+        float v = 0.0f;
+        if (qq < H) {
+            v = s0.b1[qq];
+            if (s0.P_agg) v += s0.P_agg[(size_t)node * s0.ldp_agg + qq];
+            if (s0.e_post) {
+                const float* ep = s0.e_post + (size_t)graph * ne;
+                for (int c = 0; c < ne; ++c) v = fmaf(W1e_s[qq * nep + c], ep[c], v);
             }
-            hbase[q] = v;
         }
+        hbase[qq] = v;
+    }
 
-        float acc[TR][TC];
-        float fsum[TR];
+    float acc[TR][TC];
+    float fsum[TR];
 #pragma unroll
-        for (int i = 0; i < TR; ++i) {
-            fsum[i] = 0.0f;
+    for (int i = 0; i < TR; ++i) {
+        fsum[i] = 0.0f;
 #pragma unroll
-            for (int j = 0; j < TC; ++j) acc[i][j] = 0.0f;
-        }
+        for (int j = 0; j < TC; ++j) acc[i][j] = 0.0f;
+    }
 
+    for (int s = seg0; s < seg0 + nseg; ++s) {
+        const cb_tp_segment& sg = a.segs[s];
+        const int e0 = sg.rowptr[node - sg.n0], e1 = sg.rowptr[node - sg.n0 + 1];
         for (int base = e0; base < e1; base += CH) {
             const int n = min(CH, e1 - base);
             // ---- gather raw operands of the chunk
             if (tid < n) cols_s[tid] = sg.col[base + tid] + sg.col_off;
-            __syncthreads();  // also orders hbase / previous accumulate phase
+            __syncthreads();  // also orders hbase / the previous accumulate phase
             for (int i = tid; i < n * d_in; i += THREADS) {
                 const int e = i / d_in, k = i - e * d_in;
-                xs[e * dxp + k] = a.x[(size_t)cols_s[e] * d_in + k];  // cols_s already includes col_off
+                xs[e * dxp + k] = a.x[(size_t)cols_s[e] * d_in + k];
             }
             for (int i = tid; i < n * S; i += THREADS) shs[i] = sg.sh[(size_t)base * S + i];
             for (int i = tid; i < n * ne; i += THREADS) es[i] = sg.e_attr[(size_t)base * ne + i];
@@ -160,12 +194,12 @@ tp_conv_kernel(const __grid_constant__ cb_tp_conv_args a) {
             // ---- hidden layer of the radial MLP
             {
                 const int EG = THREADS / H;  // edge groups processed concurrently
-                const int q = tid % H, eg = tid / H;
+                const int qq = tid % H, eg = tid / H;
                 if (eg < EG) {
                     for (int e = eg; e < n; e += EG) {
-                        float v = hbase[q];
-                        if (sg.P_nbr) v += sg.P_nbr[(size_t)cols_s[e] * sg.ldp_nbr + q];
-                        const float4* w4 = reinterpret_cast<const float4*>(W1e_s + q * nep);
+                        float v = hbase[qq];
+                        if (sg.P_nbr) v += sg.P_nbr[(size_t)cols_s[e] * sg.ldp_nbr + qq];
+                        const float4* w4 = reinterpret_cast<const float4*>(W1e_s + qq * nep);
                         const float4* e4 = reinterpret_cast<const float4*>(es + e * ne);
                         for (int c = 0; c < ne / 4; ++c) {
                             const float4 w = w4[c], x4 = e4[c];
@@ -174,7 +208,7 @@ tp_conv_kernel(const __grid_constant__ cb_tp_conv_args a) {
                             v = fmaf(w.z, x4.z, v);
                             v = fmaf(w.w, x4.w, v);
                         }
-                        Hs[e * HP + q] = fmaxf(v, 0.0f);
+                        Hs[e * HP + qq] = fmaxf(v, 0.0f);
                     }
                 }
             }
@@ -198,97 +232,257 @@ tp_conv_kernel(const __grid_constant__ cb_tp_conv_args a) {
 #pragma unroll
                 for (int i = 0; i < TR; ++i) fsum[i] += f[i];
             }
-            // the barrier at the top of the next chunk (after cols) protects F / Hs / xs
+            // the barrier after the next chunk's cols load protects F / Hs / xs
         }
+    }
 
-        // ---- transform: contract the tile with the second Linear (weights streamed from L2)
-        {
-            const unsigned gmask = (NCT == 32 ? 0xffffffffu : ((1u << NCT) - 1u)) << (lane & ~(NCT - 1));
+    // ---- write the finished tile: A[item][r][0..H) and column H = sum_e f_e[r]
+    float* Aout = a.workspace + (size_t)item * n_rows * HA;
 #pragma unroll
-            for (int i = 0; i < TR; ++i) {
-                const int r = tr * TR + i;
-                if (r < n_rows) {  // uniform across the NCT lanes sharing tr
-                    const cb_tp_row rw = rows_s[r];
-                    for (int m = 0; m < rw.mul; ++m) {
-                        const float* wp = sg.W2 + (size_t)(rw.w_base + m) * H + tc * TC;
-                        float sacc = 0.0f;
+    for (int i = 0; i < TR; ++i) {
+        const int r = tr * TR + i;
+        if (r < n_rows) {
+            float* dst = Aout + (size_t)r * HA + tc * TC;
 #pragma unroll
-                        for (int j4 = 0; j4 < TC / 4; ++j4) {
-                            if (tc * TC + 4 * j4 < H) {
-                                const float4 w = __ldg(reinterpret_cast<const float4*>(wp) + j4);
-                                sacc = fmaf(w.x, acc[i][4 * j4 + 0], sacc);
-                                sacc = fmaf(w.y, acc[i][4 * j4 + 1], sacc);
-                                sacc = fmaf(w.z, acc[i][4 * j4 + 2], sacc);
-                                sacc = fmaf(w.w, acc[i][4 * j4 + 3], sacc);
+            for (int j4 = 0; j4 < TC / 4; ++j4)
+                if (tc * TC + 4 * j4 < H)
+                    *reinterpret_cast<float4*>(dst + 4 * j4) =
+                        make_float4(acc[i][4 * j4], acc[i][4 * j4 + 1], acc[i][4 * j4 + 2], acc[i][4 * j4 + 3]);
+            if (tc == 0) *reinterpret_cast<float4*>(Aout + (size_t)r * HA + H) = make_float4(fsum[i], 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ (b)
+constexpr int NB = 32;        // nodes per CTA
+constexpr int TT = 256;       // threads
+constexpr int MAX_RS = 4;     // rows of a run processed concurrently
+constexpr int MAX_WROWS = 64; // weight rows staged per row group (RS * mul)
+constexpr int MAX_PASS = 2;
+
+__global__ void __launch_bounds__(TT, 2)
+tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = a.H, HA = H + PADC, d_out = a.d_out, n_rows = a.n_rows;
+    float* As = sm;                                 // [MAX_RS][NB][HA]   (aliased by the rs-reduction buffer)
+    float* Ws = As + MAX_RS * NB * HA;              // [MAX_WROWS][HA]
+    float* outacc = Ws + MAX_WROWS * HA;            // [NB][d_out]
+    __shared__ SlotTable st;
+    __shared__ int item_s[NB], deg_tot[NB];
+    __shared__ int any_valid;
+
+    const int tid = threadIdx.x;
+    const int t0 = a.node_begin + blockIdx.x * NB;
+    if (tid == 0) build_slots(a, st);
+    for (int i = tid; i < NB * d_out; i += TT) outacc[i] = 0.0f;
+    if (tid < NB) deg_tot[tid] = 0;
+    __syncthreads();
+
+    for (int q = 0; q < st.n_slots; ++q) {
+        if (t0 + NB <= st.lo[q] || t0 >= st.hi[q]) continue;   // block-uniform
+        if (tid == 0) any_valid = 0;
+        __syncthreads();
+        if (tid < NB) {
+            const int node = t0 + tid;
+            int deg = 0;
+            if (node >= st.lo[q] && node < st.hi[q]) {
+                for (int s = st.first_seg[q]; s < st.first_seg[q] + st.n_segs[q]; ++s) {
+                    const cb_tp_segment& sg = a.segs[s];
+                    deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
+                }
+            }
+            item_s[tid] = deg > 0 ? st.item_off[q] + (node - st.lo[q]) : -1;
+            deg_tot[tid] += deg;
+            if (deg > 0) any_valid = 1;
+        }
+        __syncthreads();
+        const int slot_has_edges = any_valid;
+        __syncthreads();  // everyone has read the flag before the next slot resets it
+        if (!slot_has_edges) continue;
+        const cb_tp_segment& s0 = a.segs[st.first_seg[q]];
+
+        for (int ri = 0; ri < a.n_runs; ++ri) {
+            const cb_tp_run run = a.runs[ri];
+            const int mul = run.mul;
+            const int MT = mul >= 4 ? 4 : mul;                    // outputs per work item
+            const int MC = (mul + MT - 1) / MT;                   // items per (row, node)
+            int RS = TT / (NB * MC);
+            RS = RS < 1 ? 1 : (RS > MAX_RS ? MAX_RS : RS);
+            if (RS * mul > MAX_WROWS) RS = MAX_WROWS / mul;
+            const int n_items = RS * NB * MC;
+            float acc[MAX_PASS][4];
+#pragma unroll
+            for (int p = 0; p < MAX_PASS; ++p)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[p][k] = 0.0f;
+
+            for (int rg = run.row_begin; rg < run.row_end; rg += RS) {
+                const int nrs = min(RS, run.row_end - rg);
+                __syncthreads();  // previous group fully consumed
+                // ---- stage A rows [nrs][NB][HA] (zeros for nodes without edges in this slot)
+                const int a4 = HA / 4;
+                for (int i = tid; i < nrs * NB * a4; i += TT) {
+                    const int c4 = i % a4, n = (i / a4) % NB, rs = i / (a4 * NB);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int it = item_s[n];
+                    if (it >= 0)
+                        v = __ldg(reinterpret_cast<const float4*>(a.workspace + ((size_t)it * n_rows + rg + rs) * HA) + c4);
+                    *reinterpret_cast<float4*>(As + (rs * NB + n) * HA + 4 * c4) = v;
+                }
+                // ---- stage weight rows: W2[w_base0 + (rg - row_begin + rs)*mul + m][0..H), column H = b2
+                const int wrow0 = run.w_base0 + (rg - run.row_begin) * mul;
+                const int h4 = H / 4;
+                for (int i = tid; i < nrs * mul * h4; i += TT) {
+                    const int c4 = i % h4, wr = i / h4;
+                    *reinterpret_cast<float4*>(Ws + wr * HA + 4 * c4) =
+                        __ldg(reinterpret_cast<const float4*>(s0.W2 + (size_t)(wrow0 + wr) * H) + c4);
+                }
+                for (int wr = tid; wr < nrs * mul; wr += TT)
+                    *reinterpret_cast<float4*>(Ws + wr * HA + H) = make_float4(__ldg(s0.b2 + wrow0 + wr), 0.f, 0.f, 0.f);
+                __syncthreads();
+                // ---- each work item: one (row slot, node) x MT strided outputs, dot over the HA columns
+#pragma unroll
+                for (int p = 0; p < MAX_PASS; ++p) {
+                    const int itx = tid + p * TT;
+                    if (itx < n_items) {
+                        const int mc = itx % MC, n = (itx / MC) % NB, rs = itx / (MC * NB);
+                        if (rs < nrs) {
+                            const float4* ap = reinterpret_cast<const float4*>(As + (rs * NB + n) * HA);
+                            const float* wb = Ws + (rs * mul) * HA;
+                            for (int c4 = 0; c4 < a4; ++c4) {
+                                const float4 av = ap[c4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int m = mc + k * MC;
+                                    if (k < MT && m < mul) {
+                                        const float4 w = *reinterpret_cast<const float4*>(wb + m * HA + 4 * c4);
+                                        acc[p][k] = fmaf(av.x, w.x, acc[p][k]);
+                                        acc[p][k] = fmaf(av.y, w.y, acc[p][k]);
+                                        acc[p][k] = fmaf(av.z, w.z, acc[p][k]);
+                                        acc[p][k] = fmaf(av.w, w.w, acc[p][k]);
+                                    }
+                                }
                             }
                         }
-                        if (tc == 0) sacc = fmaf(__ldg(sg.b2 + rw.w_base + m), fsum[i], sacc);
-#pragma unroll
-                        for (int o = NCT >> 1; o > 0; o >>= 1) sacc += __shfl_xor_sync(gmask, sacc, o);
-                        if (tc == 0) P[rw.p_off + m] = sacc;
                     }
                 }
             }
+            // ---- reduce over the row slots in fixed order and add into the output channels
+            __syncthreads();
+            float* part = As;  // [RS][NB][mul]
+#pragma unroll
+            for (int p = 0; p < MAX_PASS; ++p) {
+                const int itx = tid + p * TT;
+                if (itx < n_items) {
+                    const int mc = itx % MC, n = (itx / MC) % NB, rs = itx / (MC * NB);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int m = mc + k * MC;
+                        if (k < MT && m < mul) part[(rs * NB + n) * mul + m] = acc[p][k];
+                    }
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < NB * mul; i += TT) {
+                const int m = i % mul, n = i / mul;
+                float v = 0.0f;
+                for (int rs = 0; rs < RS; ++rs) v += part[(rs * NB + n) * mul + m];
+                outacc[n * d_out + run.out_base + m * run.out_step] += v;
+            }
         }
-        __syncthreads();
-        // ---- fixed-order reduction of the partial sums into the output channels
-        for (int o = warp; o < a.d_out; o += THREADS / 32) {
-            const int p0 = a.out_ptr[o], p1 = a.out_ptr[o + 1];
-            float v = 0.0f;
-            for (int p = p0 + lane; p < p1; p += 32) v += P[a.out_idx[p]];
-            v = cb_warp_sum(v);
-            if (lane == 0) outacc[o] += v;
-        }
-        __syncthreads();
     }
-
+    __syncthreads();
     // ---- epilogue: mean over all incoming edges, BatchNorm (eval) affine, residual
-    const float inv_deg = 1.0f / (float)max(deg_total, 1);
-    for (int o = tid; o < a.d_out; o += THREADS) {
-        float v = outacc[o] * inv_deg;
-        if (a.bn_scale) v = fmaf(v, a.bn_scale[o], a.bn_shift[o]);
-        if (a.residual && o < a.d_res) v += a.residual[(size_t)node * a.ld_res + o];
-        a.out[(size_t)node * a.d_out + o] = v;
+    for (int i = tid; i < NB * d_out; i += TT) {
+        const int n = i / d_out, o = i - n * d_out;
+        const int node = t0 + n;
+        if (node < a.node_end) {
+            float v = outacc[i] / (float)max(deg_tot[n], 1);
+            if (a.bn_scale) v = fmaf(v, a.bn_scale[o], a.bn_shift[o]);
+            if (a.residual && o < a.d_res) v += a.residual[(size_t)node * a.ld_res + o];
+            a.out[(size_t)node * d_out + o] = v;
+        }
     }
 }
 
 template <class C>
-int launch(const cb_tp_conv_args* a, cudaStream_t st) {
-    const SmemLayout L = make_layout(a->n_rows, a->n_terms, a->ne, a->d_in, a->S, a->n_slots, a->d_out, C::RP, C::HP);
+int launch_accumulate(const cb_tp_conv_args* a, int items, cudaStream_t st) {
+    const SmemLayout L = make_layout(a->n_rows, a->n_terms, a->ne, a->d_in, a->S, C::RP, C::HP);
     const size_t smem = (size_t)L.total * 4;
-    CB_CHECK_ARG(smem <= 227 * 1024, "cb_tp_conv_forward: needs %zu B of shared memory", smem);
-    cudaError_t e = cudaFuncSetAttribute(tp_conv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CB_CHECK_ARG(smem <= 220 * 1024, "cb_tp_conv_forward: accumulate kernel needs %zu B of shared memory", smem);
+    cudaError_t e = cudaFuncSetAttribute(tp_accumulate_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         cb_set_error("cb_tp_conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return CB_ERR_CUDA;
     }
-    tp_conv_kernel<C><<<a->n_out, C::THREADS, smem, st>>>(*a);
-    CB_CHECK_LAUNCH("cb_tp_conv_forward");
+    tp_accumulate_kernel<C><<<items, C::THREADS, smem, st>>>(*a);
+    CB_CHECK_LAUNCH("cb_tp_conv_forward(accumulate)");
     return CB_OK;
 }
 
 }  // namespace
 
+extern "C" int64_t cb_tp_conv_items(const cb_tp_conv_args* a) {
+    if (a == nullptr || a->n_segs < 0 || a->n_segs > CB_MAX_SEGS) return -1;
+    SlotTable t;
+    build_slots(*a, t);
+    return t.item_off[t.n_slots];
+}
+
 extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
     CB_CHECK_ARG(a != nullptr, "cb_tp_conv_forward: null args");
-    if (a->n_out <= 0) return CB_OK;
-    CB_CHECK_ARG(a->x && a->rows && a->terms && a->out_ptr && a->out_idx && a->out, "cb_tp_conv_forward: null pointer");
+    if (a->n_out <= 0 || a->node_end <= a->node_begin) return CB_OK;
+    CB_CHECK_ARG(a->x && a->rows && a->terms && a->runs && a->out, "cb_tp_conv_forward: null pointer");
     CB_CHECK_ARG(a->n_segs >= 0 && a->n_segs <= CB_MAX_SEGS, "cb_tp_conv_forward: n_segs=%d", a->n_segs);
     CB_CHECK_ARG(a->H > 0 && a->H % 4 == 0 && a->ne > 0 && a->ne % 4 == 0, "cb_tp_conv_forward: H=%d ne=%d must be multiples of 4",
                  a->H, a->ne);
-    CB_CHECK_ARG(a->n_rows > 0 && a->n_slots > 0 && a->d_out > 0 && a->d_in > 0 && a->S > 0, "cb_tp_conv_forward: bad sizes");
+    CB_CHECK_ARG(a->n_rows > 0 && a->n_runs > 0 && a->d_out > 0 && a->d_in > 0 && a->S > 0, "cb_tp_conv_forward: bad sizes");
     CB_CHECK_ARG((a->bn_scale == nullptr) == (a->bn_shift == nullptr), "cb_tp_conv_forward: bn_scale/bn_shift must come together");
+    CB_CHECK_ARG(0 <= a->node_begin && a->node_end <= a->n_out, "cb_tp_conv_forward: node range [%d,%d) outside [0,%d)",
+                 a->node_begin, a->node_end, a->n_out);
     for (int s = 0; s < a->n_segs; ++s) {
         const cb_tp_segment& g = a->segs[s];
         CB_CHECK_ARG(g.rowptr && g.col && g.e_attr && g.sh && g.W1e && g.b1 && g.W2 && g.b2, "cb_tp_conv_forward: segment %d has a null pointer", s);
         CB_CHECK_ARG(0 <= g.n0 && g.n0 <= g.n1 && g.n1 <= a->n_out, "cb_tp_conv_forward: segment %d node range [%d,%d) outside [0,%d)", s, g.n0, g.n1, a->n_out);
+        if (s > 0) {
+            const cb_tp_segment& p = a->segs[s - 1];
+            CB_CHECK_ARG(g.slot == p.slot || g.slot == p.slot + 1, "cb_tp_conv_forward: slots must be consecutive in segment order");
+            if (g.slot == p.slot)
+                CB_CHECK_ARG(g.n0 == p.n0 && g.n1 == p.n1 && g.W2 == p.W2 && g.W1e == p.W1e && g.P_agg == p.P_agg && g.e_post == p.e_post,
+                             "cb_tp_conv_forward: segments of slot %d must share node range and radial MLP", g.slot);
+        } else {
+            CB_CHECK_ARG(g.slot == 0, "cb_tp_conv_forward: first segment must be slot 0");
+        }
     }
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t items = cb_tp_conv_items(a);
     const int H = a->H, R = a->n_rows;
-    if (H <= 64 && R <= 256) return launch<Cfg<64, 8, 4, 8>>(a, st);
-    if (H <= 96 && R <= 256) return launch<Cfg<64, 8, 4, 12>>(a, st);
-    if (H <= 80 && R <= 320) return launch<Cfg<80, 4, 4, 20>>(a, st);
-    if (H <= 96 && R <= 320) return launch<Cfg<80, 8, 4, 12>>(a, st);
-    CB_CHECK_ARG(false, "cb_tp_conv_forward: no tile configuration for H=%d rows=%d", H, R);
-    return CB_ERR_ARG;
+    if (items > 0) {
+        CB_CHECK_ARG(a->workspace != nullptr && a->workspace_floats >= items * (int64_t)R * (H + PADC),
+                     "cb_tp_conv_forward: workspace too small (%lld floats for %lld accumulators)",
+                     (long long)a->workspace_floats, (long long)items);
+        int rc;
+        if (H <= 64 && R <= 256) rc = launch_accumulate<Cfg<64, 8, 4, 8>>(a, (int)items, st);
+        else if (H <= 96 && R <= 256) rc = launch_accumulate<Cfg<64, 8, 4, 12>>(a, (int)items, st);
+        else if (H <= 80 && R <= 320) rc = launch_accumulate<Cfg<80, 4, 4, 20>>(a, (int)items, st);
+        else if (H <= 96 && R <= 320) rc = launch_accumulate<Cfg<80, 8, 4, 12>>(a, (int)items, st);
+        else {
+            CB_CHECK_ARG(false, "cb_tp_conv_forward: no tile configuration for H=%d rows=%d", H, R);
+            return CB_ERR_ARG;
+        }
+        if (rc != CB_OK) return rc;
+    }
+    // transform + epilogue
+    const int HA = H + PADC;
+    const size_t smem = sizeof(float) * ((size_t)MAX_RS * NB * HA + (size_t)MAX_WROWS * HA + (size_t)NB * a->d_out);
+    CB_CHECK_ARG(smem <= 110 * 1024, "cb_tp_conv_forward: transform kernel needs %zu B of shared memory", smem);
+    cudaError_t e = cudaFuncSetAttribute(tp_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        cb_set_error("cb_tp_conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return CB_ERR_CUDA;
+    }
+    const int tiles = cb_div_up(a->node_end - a->node_begin, NB);
+    tp_transform_kernel<<<tiles, TT, smem, st>>>(*a);
+    CB_CHECK_LAUNCH("cb_tp_conv_forward(transform)");
+    return CB_OK;
 }

@@ -28,6 +28,10 @@ import numpy as np
 ROW_DTYPE = np.dtype([("term_begin", "<i4"), ("term_end", "<i4"), ("w_base", "<i4"), ("out_base", "<i4"),
                       ("out_step", "<i4"), ("mul", "<i4"), ("p_off", "<i4"), ("pad", "<i4")])
 TERM_DTYPE = np.dtype([("x_idx", "<i2"), ("sh_idx", "<i2"), ("coef", "<f4")])
+# a run = consecutive f-rows feeding the same output channels (same out_base/out_step/mul) whose weight rows
+# are contiguous: row r of the run uses weight rows w_base0 + (r - row_begin) * mul + m
+RUN_DTYPE = np.dtype([("row_begin", "<i4"), ("row_end", "<i4"), ("out_base", "<i4"), ("out_step", "<i4"),
+                      ("mul", "<i4"), ("w_base0", "<i4"), ("pad0", "<i4"), ("pad1", "<i4")])
 
 
 def parse_irreps(spec) -> List[Tuple[int, int, int]]:
@@ -132,6 +136,7 @@ class TPProgram:
     d_in: int
     d_out: int
     sh_dim: int
+    runs: np.ndarray = None  # RUN_DTYPE [n_runs]
 
     @property
     def n_rows(self):
@@ -166,7 +171,16 @@ class _Builder:
         out_ptr = np.zeros(d_out + 1, dtype=np.int32)
         out_ptr[1:] = np.cumsum([len(s) for s in slots])
         out_idx = np.asarray([q for s in slots for q in s], dtype=np.int32)
-        return TPProgram(rows, terms, out_ptr, out_idx, int(weight_numel), int(d_in), int(d_out), int(sh_dim))
+        runs = []
+        for r, (_, _, wb, ob, os_, mul) in enumerate(self.rows):
+            if runs and runs[-1][2:5] == [ob, os_, mul] and wb == runs[-1][5] + (r - runs[-1][0]) * mul:
+                runs[-1][1] = r + 1
+            else:
+                runs.append([r, r + 1, ob, os_, mul, wb])
+        run_arr = np.zeros(len(runs), dtype=RUN_DTYPE)
+        for k, (rb, re_, ob, os_, mul, wb) in enumerate(runs):
+            run_arr[k] = (rb, re_, ob, os_, mul, wb, 0, 0)
+        return TPProgram(rows, terms, out_ptr, out_idx, int(weight_numel), int(d_in), int(d_out), int(sh_dim), run_arr)
 
 
 def _offsets(irreps):
@@ -226,9 +240,9 @@ def faster_tp_program(in_irreps, out_irreps) -> TPProgram:
         if mul_out > 0:
             assert len(inter[k]) == fan[k]
             scale = 1.0 / math.sqrt(fan[k])
-            for i, comps in enumerate(inter[k]):
-                for c, terms in enumerate(comps):
-                    b.row([(x, s, v * scale) for (x, s, v) in terms], start + i * mul_out, o_off + c, dim, mul_out)
+            for c in range(dim):          # component-major: consecutive rows share their output channels
+                for i, comps in enumerate(inter[k]):
+                    b.row([(x, s, v * scale) for (x, s, v) in comps[c]], start + i * mul_out, o_off + c, dim, mul_out)
         start += fan[k] * mul_out
     return b.finish(start, d_in, d_out, 4)
 
@@ -255,8 +269,8 @@ def fctp_program(in_irreps, sh_irreps_, out_irreps) -> TPProgram:
             raise NotImplementedError("edge harmonics always have multiplicity 1 on this path")
         alpha = math.sqrt((2 * lo + 1) / fan[io])
         w3 = wigner_3j(l1, l2, lo)
-        for u in range(m1):
-            for k in range(2 * lo + 1):
+        for k in range(2 * lo + 1):       # component-major: consecutive rows share their output channels
+            for u in range(m1):
                 terms = [(in_off[i1] + u * (2 * l1 + 1) + i, sh_off[i2] + j, alpha * w3[i, j, k])
                          for i in range(2 * l1 + 1) for j in range(2 * l2 + 1) if abs(w3[i, j, k]) > 1e-12]
                 b.row(terms, woff + u * mo, out_off[io] + k, 2 * lo + 1, mo)

@@ -21,6 +21,7 @@ from .irreps import (TPProgram, faster_tp_program, fctp_program, get_irrep_seq, 
                      parse_irreps, sh_irreps)
 
 ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
+WORKSPACE_BYTES = 6 << 30  # cap on the K3 accumulator workspace; larger layers are processed in node chunks
 
 
 def FCBlock(in_dim, hidden_dim, out_dim, layers, dropout, activation="relu"):
@@ -80,6 +81,7 @@ class Segment:
     n1: int = 0
     col_off: int = 0                     # offset of the neighbour node type inside x
     e_post: Optional[torch.Tensor] = None  # [B, ne]
+    slot: Optional[int] = None           # segments sharing a slot share (n0, n1, group) and one accumulator
 
 
 class _DeviceProgram:
@@ -87,8 +89,8 @@ class _DeviceProgram:
         self.prog = prog
         self.rows = torch.from_numpy(prog.rows.view(np.uint8).copy()).to(device)
         self.terms = torch.from_numpy(prog.terms.view(np.uint8).copy()).to(device)
-        self.out_ptr = torch.from_numpy(prog.out_ptr).to(device)
-        self.out_idx = torch.from_numpy(prog.out_idx).to(device)
+        self.runs = torch.from_numpy(prog.runs.view(np.uint8).copy()).to(device)
+        assert int(prog.runs["mul"].max()) <= 64, "transform kernel stages at most 64 weight rows per row group"
 
 
 class TensorProductConvLayer(nn.Module):
@@ -177,9 +179,15 @@ class TensorProductConvLayer(nn.Module):
         a.agg_graph = _lib.i32(agg_graph, "agg_graph", allow_none=True)
         a.rows, a.n_rows = dp.rows.data_ptr(), P.n_rows
         a.terms, a.n_terms = dp.terms.data_ptr(), len(P.terms)
-        a.out_ptr, a.out_idx, a.n_slots = dp.out_ptr.data_ptr(), dp.out_idx.data_ptr(), P.n_slots
+        a.runs, a.n_runs = dp.runs.data_ptr(), len(P.runs)
         a.n_segs = len(segments)
         keep = []
+        # slots: explicit ids, else one slot per run of adjacent segments with equal (group, n0, n1, e_post)
+        slot_ids, prev = [], None
+        for s in segments:
+            key = (s.group, s.n0, s.n1, None if s.e_post is None else s.e_post.data_ptr()) if s.slot is None else ("id", s.slot)
+            slot_ids.append(slot_ids[-1] + (key != prev) if slot_ids else 0)
+            prev = key
         for k, s in enumerate(segments):
             fc = self._fc(s.group)
             W1, b1, W2, b2 = fc[0].weight, fc[0].bias, fc[3].weight, fc[3].bias
@@ -196,7 +204,7 @@ class TensorProductConvLayer(nn.Module):
                 sg.P_nbr, sg.ldp_nbr = t.data_ptr() + 4 * off, t.shape[1]
             sg.W1e, sg.ldw1 = _lib.f32(W1, "W1") + 4 * e_cols[0], W1.shape[1]
             sg.b1, sg.W2, sg.b2 = _lib.f32(b1, "b1"), _lib.f32(W2, "W2"), _lib.f32(b2, "b2")
-            sg.n0, sg.n1, sg.col_off = s.n0, s.n1, s.col_off
+            sg.n0, sg.n1, sg.col_off, sg.slot = s.n0, s.n1, s.col_off, slot_ids[k]
         if self.batch_norm is not None:
             scale, shift = self.batch_norm.affine()
             a.bn_scale, a.bn_shift = scale.data_ptr(), shift.data_ptr()
@@ -207,7 +215,19 @@ class TensorProductConvLayer(nn.Module):
         # bookkeeping for profilers (bench.py): which edge counters / sizes this launch covers
         a._meta = dict(layer=self, n_in=int(x.shape[0]), n_out=int(n_out), groups=groups,
                        edge_counters=[s.edges.n_edges_dev for s in segments])
-        _lib.tp_conv_forward(a)
+        # workspace: one R x (H+4) accumulator per (node, slot); process the nodes in chunks if it would be huge
+        per_item = P.n_rows * (H + 4)
+        a.node_begin, a.node_end = 0, n_out
+        items = _lib.tp_conv_items(a)
+        max_items = max(1, WORKSPACE_BYTES // (4 * per_item))
+        n_chunks = max(1, -(-items // max_items))
+        step = -(-n_out // n_chunks)
+        for c0 in range(0, n_out, step):
+            a.node_begin, a.node_end = c0, min(n_out, c0 + step)
+            it = _lib.tp_conv_items(a)
+            ws = torch.empty(max(it, 1) * per_item, dtype=torch.float32, device=dev)
+            a.workspace, a.workspace_floats = ws.data_ptr(), ws.numel()
+            _lib.tp_conv_forward(a)
         return out
 
     # ------------------------------------------------------------------ reference-style call

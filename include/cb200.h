@@ -24,7 +24,7 @@ extern "C" {
 const char* cb_last_error(void);
 int cb_version(void);
 /* sizeof of the argument structs, for binding self-checks: 0 edge_feat, 1 tp_segment, 2 tp_conv, 3 sde_step,
- * 4 tp_row, 5 tp_term, 6 crop */
+ * 4 tp_row, 5 tp_term, 6 tp_run */
 int cb_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------ K1
@@ -108,6 +108,9 @@ int cb_edge_featurize(const cb_edge_feat_args* a, void* stream);
  * edge segment s,   sum_e tp_e = T_s( sum_e f_e (x) [h_e ; 1] ),   f_e = CG products of x[col[e]]
  * and sh_e (the "program"), h_e = relu(b1 + P_agg[i] + P_nbr[col[e]] + W1e (e_attr[e] + e_post[g(i)])),
  * T_s = contraction with (W2, b2).  The [E, weight_numel] tensor is never materialised.
+ * Two launches: (a) accumulate, one CTA per (node, slot), A = sum_e f_e (x) [h_e;1] in registers, written
+ * once to the workspace; (b) transform + epilogue, one CTA per 32 nodes, which streams every W2 row once
+ * per 32 nodes and finishes with mean / BatchNorm / residual.
  */
 typedef struct {            /* one CG product term of an f-row: coef * x[x_idx] * sh[sh_idx] */
     int16_t x_idx; int16_t sh_idx; float coef;
@@ -118,9 +121,14 @@ typedef struct {            /* one f-row (intermediate channel feeding one outpu
     int32_t out_base;       /* output channel for multiplicity m is out_base + m*out_step        */
     int32_t out_step;
     int32_t mul;            /* number of output multiplicities fed by this row                   */
-    int32_t p_off;          /* first partial-sum slot of this row (prefix sum of mul)            */
+    int32_t p_off;          /* prefix sum of mul (kept for evaluators / tests)                   */
     int32_t pad_;
 } cb_tp_row;
+typedef struct {            /* consecutive rows feeding the same outputs, with contiguous weight rows: */
+    int32_t row_begin, row_end;   /* row r uses weight rows w_base0 + (r-row_begin)*mul + m, m < mul   */
+    int32_t out_base, out_step, mul, w_base0;
+    int32_t pad0_, pad1_;
+} cb_tp_run;
 typedef struct {
     const int32_t* rowptr;  /* CSR over aggregation nodes: edges of node i are rowptr[i-n0]..rowptr[i-n0+1] */
     const int32_t* col;     /* [E] neighbour index into x                                       */
@@ -137,7 +145,8 @@ typedef struct {
     const float* b2;        /* [weight_numel]                                                   */
     int32_t n0, n1;         /* aggregation-node range served by this segment                    */
     int32_t col_off;        /* added to col[e] to index x / P_nbr (node tables are concatenated)  */
-    int32_t pad_;
+    int32_t slot;           /* segments with the same slot share (n0,n1), the radial MLP and one accumulator;
+                               slots are numbered 0.. in segment order, equal slots adjacent        */
 } cb_tp_segment;
 #define CB_MAX_SEGS 12
 typedef struct {
@@ -147,9 +156,7 @@ typedef struct {
     const int32_t* agg_graph; /* [n_out] graph id (for e_post) or NULL                           */
     const cb_tp_row* rows; int32_t n_rows;   /* device tables built once per layer               */
     const cb_tp_term* terms; int32_t n_terms;
-    const int32_t* out_ptr;  /* [d_out+1] CSR: partial-sum slots feeding every output channel     */
-    const int32_t* out_idx;  /* [n_slots]                                                        */
-    int32_t n_slots;         /* sum over rows of mul                                             */
+    const cb_tp_run* runs; int32_t n_runs;
     int32_t n_segs;
     cb_tp_segment segs[CB_MAX_SEGS];
     /* epilogue: mean over all segments, BatchNorm(eval) affine, residual                         */
@@ -158,7 +165,13 @@ typedef struct {
     const float* residual;  /* [n_out, ld_res] added to the first d_res channels, or NULL        */
     int32_t d_res, ld_res;
     float* out;             /* [n_out, d_out]                                                    */
+    /* workspace for the per-(node, slot) accumulators A[item][n_rows][H+4]; the call processes the
+     * aggregation nodes [node_begin, node_end) and needs cb_tp_conv_items(a) * n_rows * (H+4) floats   */
+    float* workspace; int64_t workspace_floats;
+    int32_t node_begin, node_end;
 } cb_tp_conv_args;
+/* number of (node, slot) accumulators the call will use (host arithmetic only) */
+int64_t cb_tp_conv_items(const cb_tp_conv_args* a);
 int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------ K4

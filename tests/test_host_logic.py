@@ -82,11 +82,12 @@ def test_cabi_exports_and_struct_layout():
     lib = _lib.lib()
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in cb200.h but not exported"
-    assert set(_lib.EXPORTS) == declared
+    assert set(_lib.EXPORTS) == declared, set(_lib.EXPORTS) ^ declared
     assert lib.cb_version() >= 100
     for which, struct in enumerate([_lib.EdgeFeatArgs, _lib.TpSegment, _lib.TpConvArgs, _lib.SdeStepArgs]):
         assert lib.cb_sizeof(which) == ctypes.sizeof(struct)
     assert lib.cb_sizeof(4) == irreps.ROW_DTYPE.itemsize and lib.cb_sizeof(5) == irreps.TERM_DTYPE.itemsize
+    assert lib.cb_sizeof(6) == irreps.RUN_DTYPE.itemsize
 
 
 def test_wrappers_refuse_cpu_tensors():
