@@ -88,7 +88,7 @@ __host__ __device__ inline SmemLayout make_layout(int n_rows, int n_terms, int n
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
-tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a) {
+tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
     constexpr int NCT = C::NCT, TR = C::TR, TC = C::TC, RP = C::RP, HP = C::HP, THREADS = C::THREADS;
     static_assert(TR == 4 && TC % 4 == 0, "tile shape");
     extern __shared__ __align__(16) float sm[];
@@ -105,28 +105,13 @@ tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a) {
     float* Hs = sm + L.Hs;
     __shared__ SlotTable st;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tr = tid / NCT, tc = tid % NCT;
     const int H = a.H, ne = a.ne, S = a.S, d_in = a.d_in, n_rows = a.n_rows, nep = L.nep, dxp = L.dxp;
     const int HA = H + PADC;
 
+    // once per (persistent) CTA: slot table, TP program, zeroed padding of the staging tiles
     if (tid == 0) build_slots(a, st);
-    __syncthreads();
-    // item -> (slot, node)
-    int q = 0;
-    const int item = blockIdx.x;
-    while (q + 1 < st.n_slots && item >= st.item_off[q + 1]) ++q;
-    const int node = st.lo[q] + (item - st.item_off[q]);
-    const int seg0 = st.first_seg[q], nseg = st.n_segs[q];
-    int deg = 0;
-    for (int s = seg0; s < seg0 + nseg; ++s) {
-        const cb_tp_segment& sg = a.segs[s];
-        deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
-    }
-    if (deg == 0) return;  // block-uniform; the transform kernel skips (node, slot) pairs without edges
-
-    // one-time staging: TP program, zeroed tiles, slot-level MLP pieces
-    const cb_tp_segment& s0 = a.segs[seg0];
     {
         const int* src = reinterpret_cast<const int*>(a.rows);
         int* dst = reinterpret_cast<int*>(rows_s);
@@ -136,119 +121,171 @@ tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a) {
         for (int i = tid; i < a.n_terms; i += THREADS) tdst[i] = tsrc[i];
         for (int i = tid; i < CH * RP; i += THREADS) F[i] = 0.0f;
         for (int i = tid; i < CH * HP; i += THREADS) Hs[i] = 0.0f;
-        for (int i = tid; i < HP * ne; i += THREADS) {
-            const int qq = i / ne, c = i - qq * ne;
-            W1e_s[qq * nep + c] = qq < H ? s0.W1e[(size_t)qq * s0.ldw1 + c] : 0.0f;
-        }
     }
-    const int graph = a.agg_graph ? a.agg_graph[node] : 0;
     __syncthreads();
-    for (int qq = tid; qq < HP; qq += THREADS) {
-        float v = 0.0f;
-        if (qq < H) {
-            v = s0.b1[qq];
-            if (s0.P_agg) v += s0.P_agg[(size_t)node * s0.ldp_agg + qq];
-            if (s0.e_post) {
-                const float* ep = s0.e_post + (size_t)graph * ne;
-                for (int c = 0; c < ne; ++c) v = fmaf(W1e_s[qq * nep + c], ep[c], v);
-            }
+    // f-rows: thread -> fixed row, strided over the chunk's edges
+    const int my_row = tid % RP, my_par = tid / RP;
+    constexpr int EP = THREADS / RP > 0 ? THREADS / RP : 1;
+    constexpr int MAXT = 4;  // terms of the thread's row kept in registers (longer rows finish from smem)
+    int tb = 0, te = 0, t_xi[MAXT], t_si[MAXT];
+    float t_cf[MAXT];
+    const bool f_thread = my_row < n_rows && my_par < EP;
+    if (f_thread) {
+        tb = rows_s[my_row].term_begin;
+        te = rows_s[my_row].term_end;
+    }
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+        const bool on = f_thread && tb + t < te;
+        const cb_tp_term tm = on ? terms_s[tb + t] : cb_tp_term{0, 0, 0.0f};
+        t_xi[t] = tm.x_idx;
+        t_si[t] = tm.sh_idx;
+        t_cf[t] = on ? tm.coef : 0.0f;   // inactive slots multiply x[0]*sh[0] by zero
+    }
+    int staged_slot = -1;
+    int q = 0;  // items are visited in increasing order: the slot index only moves forward
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        // item -> (slot, node)
+        while (q + 1 < st.n_slots && item >= st.item_off[q + 1]) ++q;
+        const int node = st.lo[q] + (item - st.item_off[q]);
+        const int seg0 = st.first_seg[q], nseg = st.n_segs[q];
+        int deg = 0;
+        for (int s = seg0; s < seg0 + nseg; ++s) {
+            const cb_tp_segment& sg = a.segs[s];
+            deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
         }
-        hbase[qq] = v;
-    }
+        if (deg == 0) continue;  // block-uniform; the transform kernel skips (node, slot) pairs without edges
 
-    float acc[TR][TC];
-    float fsum[TR];
-#pragma unroll
-    for (int i = 0; i < TR; ++i) {
-        fsum[i] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < TC; ++j) acc[i][j] = 0.0f;
-    }
-
-    for (int s = seg0; s < seg0 + nseg; ++s) {
-        const cb_tp_segment& sg = a.segs[s];
-        const int e0 = sg.rowptr[node - sg.n0], e1 = sg.rowptr[node - sg.n0 + 1];
-        for (int base = e0; base < e1; base += CH) {
-            const int n = min(CH, e1 - base);
-            // ---- gather raw operands of the chunk
-            if (tid < n) cols_s[tid] = sg.col[base + tid] + sg.col_off;
-            __syncthreads();  // also orders hbase / the previous accumulate phase
-            for (int i = tid; i < n * d_in; i += THREADS) {
-                const int e = i / d_in, k = i - e * d_in;
-                xs[e * dxp + k] = a.x[(size_t)cols_s[e] * d_in + k];
+        const cb_tp_segment& s0 = a.segs[seg0];
+        __syncthreads();  // previous item's h-phase readers of W1e_s / hbase are done
+        if (staged_slot != q) {
+            for (int i = tid; i < HP * (ne / 4); i += THREADS) {
+                const int qq = i / (ne / 4), c4 = i - qq * (ne / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qq < H) v = __ldg(reinterpret_cast<const float4*>(s0.W1e + (size_t)qq * s0.ldw1) + c4);
+                *reinterpret_cast<float4*>(W1e_s + qq * nep + 4 * c4) = v;
             }
-            for (int i = tid; i < n * S; i += THREADS) shs[i] = sg.sh[(size_t)base * S + i];
-            for (int i = tid; i < n * ne; i += THREADS) es[i] = sg.e_attr[(size_t)base * ne + i];
+            staged_slot = q;
             __syncthreads();
-            // ---- f rows: CG products of the gathered node features with the edge harmonics
-            for (int i = tid; i < n * n_rows; i += THREADS) {
-                const int e = i / n_rows, r = i - e * n_rows;
-                const int tb = rows_s[r].term_begin, te = rows_s[r].term_end;
-                float v = 0.0f;
-                for (int t = tb; t < te; ++t) {
-                    const cb_tp_term tm = terms_s[t];
-                    v = fmaf(tm.coef * xs[e * dxp + tm.x_idx], shs[e * S + tm.sh_idx], v);
+        }
+        const int graph = a.agg_graph ? a.agg_graph[node] : 0;
+        for (int qq = tid; qq < HP; qq += THREADS) {
+            float v = 0.0f;
+            if (qq < H) {
+                v = s0.b1[qq];
+                if (s0.P_agg) v += s0.P_agg[(size_t)node * s0.ldp_agg + qq];
+                if (s0.e_post) {
+                    const float* ep = s0.e_post + (size_t)graph * ne;
+                    for (int c = 0; c < ne; ++c) v = fmaf(W1e_s[qq * nep + c], ep[c], v);
                 }
-                F[e * RP + r] = v;
             }
-            // ---- hidden layer of the radial MLP
-            {
-                const int EG = THREADS / H;  // edge groups processed concurrently
-                const int qq = tid % H, eg = tid / H;
-                if (eg < EG) {
-                    for (int e = eg; e < n; e += EG) {
-                        float v = hbase[qq];
-                        if (sg.P_nbr) v += sg.P_nbr[(size_t)cols_s[e] * sg.ldp_nbr + qq];
-                        const float4* w4 = reinterpret_cast<const float4*>(W1e_s + qq * nep);
-                        const float4* e4 = reinterpret_cast<const float4*>(es + e * ne);
-                        for (int c = 0; c < ne / 4; ++c) {
-                            const float4 w = w4[c], x4 = e4[c];
-                            v = fmaf(w.x, x4.x, v);
-                            v = fmaf(w.y, x4.y, v);
-                            v = fmaf(w.z, x4.z, v);
-                            v = fmaf(w.w, x4.w, v);
+            hbase[qq] = v;
+        }
+
+        float acc[TR][TC];
+        float fsum[TR];
+#pragma unroll
+        for (int i = 0; i < TR; ++i) {
+            fsum[i] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < TC; ++j) acc[i][j] = 0.0f;
+        }
+
+        for (int s = seg0; s < seg0 + nseg; ++s) {
+            const cb_tp_segment& sg = a.segs[s];
+            const int e0 = sg.rowptr[node - sg.n0], e1 = sg.rowptr[node - sg.n0 + 1];
+            for (int base = e0; base < e1; base += CH) {
+                const int n = min(CH, e1 - base);
+                // ---- gather raw operands of the chunk
+                if (tid < n) cols_s[tid] = sg.col[base + tid] + sg.col_off;
+                __syncthreads();  // also orders hbase / the previous accumulate phase
+                for (int e = warp; e < n; e += THREADS / 32) {
+                    const float* xr = a.x + (size_t)cols_s[e] * d_in;
+                    for (int k = lane; k < d_in; k += 32) xs[e * dxp + k] = __ldg(xr + k);
+                    if (sg.P_nbr) {  // neighbour-side projection of the first Linear, staged where h will be written
+                        const float* pr = sg.P_nbr + (size_t)cols_s[e] * sg.ldp_nbr;
+                        for (int k = lane; k < H; k += 32) Hs[e * HP + k] = __ldg(pr + k);
+                    }
+                }
+                for (int i = tid; i < n * S; i += THREADS) shs[i] = __ldg(sg.sh + (size_t)base * S + i);
+                for (int i = tid; i < n * (ne / 4); i += THREADS)
+                    reinterpret_cast<float4*>(es)[i] = __ldg(reinterpret_cast<const float4*>(sg.e_attr + (size_t)base * ne) + i);
+                __syncthreads();
+                // ---- f rows: CG products of the gathered node features with the edge harmonics
+                if (f_thread) {
+                    for (int e = my_par; e < n; e += EP) {
+                        const float* xe = xs + e * dxp;
+                        const float* se = shs + e * S;
+                        float v = 0.0f;
+#pragma unroll
+                        for (int t = 0; t < MAXT; ++t) v = fmaf(t_cf[t] * xe[t_xi[t]], se[t_si[t]], v);
+                        for (int t = tb + MAXT; t < te; ++t) {
+                            const cb_tp_term tm = terms_s[t];
+                            v = fmaf(tm.coef * xe[tm.x_idx], se[tm.sh_idx], v);
                         }
-                        Hs[e * HP + qq] = fmaxf(v, 0.0f);
+                        F[e * RP + my_row] = v;
                     }
                 }
-            }
-            __syncthreads();
-            // ---- rank-1 updates of the register tile
-#pragma unroll 2
-            for (int e = 0; e < n; ++e) {
-                const float4 f4 = *reinterpret_cast<const float4*>(F + e * RP + tr * TR);
-                const float f[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-                for (int j4 = 0; j4 < TC / 4; ++j4) {
-                    const float4 h4 = *reinterpret_cast<const float4*>(Hs + e * HP + tc * TC + 4 * j4);
-#pragma unroll
-                    for (int i = 0; i < TR; ++i) {
-                        acc[i][4 * j4 + 0] = fmaf(f[i], h4.x, acc[i][4 * j4 + 0]);
-                        acc[i][4 * j4 + 1] = fmaf(f[i], h4.y, acc[i][4 * j4 + 1]);
-                        acc[i][4 * j4 + 2] = fmaf(f[i], h4.z, acc[i][4 * j4 + 2]);
-                        acc[i][4 * j4 + 3] = fmaf(f[i], h4.w, acc[i][4 * j4 + 3]);
+                // ---- hidden layer of the radial MLP
+                {
+                    const int EG = THREADS / H;  // edge groups processed concurrently
+                    const int qq = tid % H, eg = tid / H;
+                    if (eg < EG) {
+                        const float4* w4 = reinterpret_cast<const float4*>(W1e_s + qq * nep);
+                        for (int e = eg; e < n; e += EG) {
+                            float v = hbase[qq];
+                            if (sg.P_nbr) v += Hs[e * HP + qq];
+                            const float4* e4 = reinterpret_cast<const float4*>(es + e * ne);
+                            for (int c = 0; c < ne / 4; ++c) {
+                                const float4 w = w4[c], x4 = e4[c];
+                                v = fmaf(w.x, x4.x, v);
+                                v = fmaf(w.y, x4.y, v);
+                                v = fmaf(w.z, x4.z, v);
+                                v = fmaf(w.w, x4.w, v);
+                            }
+                            Hs[e * HP + qq] = fmaxf(v, 0.0f);
+                        }
                     }
                 }
+                __syncthreads();
+                // ---- rank-1 updates of the register tile
+#pragma unroll 4
+                for (int e = 0; e < n; ++e) {
+                    const float4 f4 = *reinterpret_cast<const float4*>(F + e * RP + tr * TR);
+                    const float f[4] = {f4.x, f4.y, f4.z, f4.w};
 #pragma unroll
-                for (int i = 0; i < TR; ++i) fsum[i] += f[i];
+                    for (int j4 = 0; j4 < TC / 4; ++j4) {
+                        const float4 h4 = *reinterpret_cast<const float4*>(Hs + e * HP + tc * TC + 4 * j4);
+#pragma unroll
+                        for (int i = 0; i < TR; ++i) {
+                            acc[i][4 * j4 + 0] = fmaf(f[i], h4.x, acc[i][4 * j4 + 0]);
+                            acc[i][4 * j4 + 1] = fmaf(f[i], h4.y, acc[i][4 * j4 + 1]);
+                            acc[i][4 * j4 + 2] = fmaf(f[i], h4.z, acc[i][4 * j4 + 2]);
+                            acc[i][4 * j4 + 3] = fmaf(f[i], h4.w, acc[i][4 * j4 + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < TR; ++i) fsum[i] += f[i];
+                }
+                // the barrier after the next chunk's cols load protects F / Hs / xs
             }
-            // the barrier after the next chunk's cols load protects F / Hs / xs
         }
-    }
 
-    // ---- write the finished tile: A[item][r][0..H) and column H = sum_e f_e[r]
-    float* Aout = a.workspace + (size_t)item * n_rows * HA;
+        // ---- write the finished tile: A[item][r][0..H) and column H = sum_e f_e[r]
+        float* Aout = a.workspace + (size_t)item * n_rows * HA;
 #pragma unroll
-    for (int i = 0; i < TR; ++i) {
-        const int r = tr * TR + i;
-        if (r < n_rows) {
-            float* dst = Aout + (size_t)r * HA + tc * TC;
+        for (int i = 0; i < TR; ++i) {
+            const int r = tr * TR + i;
+            if (r < n_rows) {
+                float* dst = Aout + (size_t)r * HA + tc * TC;
 #pragma unroll
-            for (int j4 = 0; j4 < TC / 4; ++j4)
-                if (tc * TC + 4 * j4 < H)
-                    *reinterpret_cast<float4*>(dst + 4 * j4) =
-                        make_float4(acc[i][4 * j4], acc[i][4 * j4 + 1], acc[i][4 * j4 + 2], acc[i][4 * j4 + 3]);
-            if (tc == 0) *reinterpret_cast<float4*>(Aout + (size_t)r * HA + H) = make_float4(fsum[i], 0.f, 0.f, 0.f);
+                for (int j4 = 0; j4 < TC / 4; ++j4)
+                    if (tc * TC + 4 * j4 < H)
+                        *reinterpret_cast<float4*>(dst + 4 * j4) =
+                            make_float4(acc[i][4 * j4], acc[i][4 * j4 + 1], acc[i][4 * j4 + 2], acc[i][4 * j4 + 3]);
+                if (tc == 0) *reinterpret_cast<float4*>(Aout + (size_t)r * HA + H) = make_float4(fsum[i], 0.f, 0.f, 0.f);
+            }
         }
     }
 }
@@ -256,17 +293,27 @@ tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a) {
 // ------------------------------------------------------------------------------------------ (b)
 constexpr int NB = 32;        // nodes per CTA
 constexpr int TT = 256;       // threads
-constexpr int MAX_RS = 4;     // rows of a run processed concurrently
-constexpr int MAX_WROWS = 64; // weight rows staged per row group (RS * mul)
+constexpr int MAX_RS = 2;     // rows of a run processed concurrently
+constexpr int MAX_WROWS = 32; // weight rows staged per row group (RS * mul): mul <= 32
 constexpr int MAX_PASS = 2;
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 __global__ void __launch_bounds__(TT, 2)
 tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
     extern __shared__ __align__(16) float sm[];
     const int H = a.H, HA = H + PADC, d_out = a.d_out, n_rows = a.n_rows;
-    float* As = sm;                                 // [MAX_RS][NB][HA]   (aliased by the rs-reduction buffer)
-    float* Ws = As + MAX_RS * NB * HA;              // [MAX_WROWS][HA]
-    float* outacc = Ws + MAX_WROWS * HA;            // [NB][d_out]
+    const int a4 = HA / 4, h4 = H / 4;
+    const int A_STAGE = MAX_RS * NB * HA, W_STAGE = MAX_WROWS * HA;
+    float* As = sm;                                 // [2][MAX_RS][NB][HA]   (stage 0 aliased by the rs-reduction buffer)
+    float* Ws = As + 2 * A_STAGE;                   // [2][MAX_WROWS][HA]
+    float* outacc = Ws + 2 * W_STAGE;               // [NB][d_out]
     __shared__ SlotTable st;
     __shared__ int item_s[NB], deg_tot[NB];
     __shared__ int any_valid;
@@ -304,58 +351,86 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
         for (int ri = 0; ri < a.n_runs; ++ri) {
             const cb_tp_run run = a.runs[ri];
             const int mul = run.mul;
-            const int MT = mul >= 4 ? 4 : mul;                    // outputs per work item
-            const int MC = (mul + MT - 1) / MT;                   // items per (row, node)
+            // work item = (row slot, node, output chunk); MT strided outputs per item, chosen to fill the CTA
+            const int MT = mul >= 16 ? 4 : (mul >= 4 ? 2 : 1);
+            const int MC = (mul + MT - 1) / MT;
             int RS = TT / (NB * MC);
             RS = RS < 1 ? 1 : (RS > MAX_RS ? MAX_RS : RS);
-            if (RS * mul > MAX_WROWS) RS = MAX_WROWS / mul;
+            if (RS * mul > MAX_WROWS) RS = 1;
             const int n_items = RS * NB * MC;
+            const int n_groups = (run.row_end - run.row_begin + RS - 1) / RS;
             float acc[MAX_PASS][4];
 #pragma unroll
             for (int p = 0; p < MAX_PASS; ++p)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[p][k] = 0.0f;
 
-            for (int rg = run.row_begin; rg < run.row_end; rg += RS) {
+            // asynchronous staging of one row group: A rows [nrs][NB][HA] (zeros for nodes without edges in this
+            // slot) and the weight rows W2[w_base0 + (rg - row_begin + rs)*mul + m][0..H), column H = b2
+            auto prefetch = [&](int g, int buf) {
+                const int rg = run.row_begin + g * RS;
                 const int nrs = min(RS, run.row_end - rg);
-                __syncthreads();  // previous group fully consumed
-                // ---- stage A rows [nrs][NB][HA] (zeros for nodes without edges in this slot)
-                const int a4 = HA / 4;
-                for (int i = tid; i < nrs * NB * a4; i += TT) {
-                    const int c4 = i % a4, n = (i / a4) % NB, rs = i / (a4 * NB);
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                float* Ab = As + buf * A_STAGE;
+                float* Wb = Ws + buf * W_STAGE;
+                // 8 threads per staged row: no integer division in the copy loops
+                const int sub = tid & 7;
+                for (int rn = tid >> 3; rn < nrs * NB; rn += TT / 8) {
+                    const int n = rn & (NB - 1), rs = rn / NB;
+                    float* dst = Ab + rn * HA;
                     const int it = item_s[n];
-                    if (it >= 0)
-                        v = __ldg(reinterpret_cast<const float4*>(a.workspace + ((size_t)it * n_rows + rg + rs) * HA) + c4);
-                    *reinterpret_cast<float4*>(As + (rs * NB + n) * HA + 4 * c4) = v;
+                    if (it >= 0) {
+                        const float* src = a.workspace + ((size_t)it * n_rows + rg + rs) * HA;
+                        for (int c4 = sub; c4 < a4; c4 += 8) cp_async16(dst + 4 * c4, src + 4 * c4);
+                    } else {
+                        for (int c4 = sub; c4 < a4; c4 += 8) *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
-                // ---- stage weight rows: W2[w_base0 + (rg - row_begin + rs)*mul + m][0..H), column H = b2
                 const int wrow0 = run.w_base0 + (rg - run.row_begin) * mul;
-                const int h4 = H / 4;
-                for (int i = tid; i < nrs * mul * h4; i += TT) {
-                    const int c4 = i % h4, wr = i / h4;
-                    *reinterpret_cast<float4*>(Ws + wr * HA + 4 * c4) =
-                        __ldg(reinterpret_cast<const float4*>(s0.W2 + (size_t)(wrow0 + wr) * H) + c4);
+                for (int wr = tid >> 3; wr < nrs * mul; wr += TT / 8) {
+                    const float* src = s0.W2 + (size_t)(wrow0 + wr) * H;
+                    float* dst = Wb + wr * HA;
+                    for (int c4 = sub; c4 < h4; c4 += 8) cp_async16(dst + 4 * c4, src + 4 * c4);
                 }
                 for (int wr = tid; wr < nrs * mul; wr += TT)
-                    *reinterpret_cast<float4*>(Ws + wr * HA + H) = make_float4(__ldg(s0.b2 + wrow0 + wr), 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(Wb + wr * HA + H) = make_float4(__ldg(s0.b2 + wrow0 + wr), 0.f, 0.f, 0.f);
+                cp_async_commit();
+            };
+
+            __syncthreads();  // buffers free (previous run's reduction done)
+            prefetch(0, 0);
+            for (int g = 0; g < n_groups; ++g) {
+                const int buf = g & 1;
+                if (g + 1 < n_groups) {
+                    prefetch(g + 1, buf ^ 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
                 __syncthreads();
-                // ---- each work item: one (row slot, node) x MT strided outputs, dot over the HA columns
+                const int nrs = min(RS, run.row_end - (run.row_begin + g * RS));
+                const float* Ab = As + buf * A_STAGE;
+                const float* Wb = Ws + buf * W_STAGE;
 #pragma unroll
                 for (int p = 0; p < MAX_PASS; ++p) {
                     const int itx = tid + p * TT;
                     if (itx < n_items) {
                         const int mc = itx % MC, n = (itx / MC) % NB, rs = itx / (MC * NB);
                         if (rs < nrs) {
-                            const float4* ap = reinterpret_cast<const float4*>(As + (rs * NB + n) * HA);
-                            const float* wb = Ws + (rs * mul) * HA;
+                            const float4* ap = reinterpret_cast<const float4*>(Ab + (rs * NB + n) * HA);
+                            // rows of the strided outputs m = mc + k*MC; outputs beyond mul read row 0 and are discarded
+                            const float4* wp[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int m = mc + k * MC;
+                                wp[k] = reinterpret_cast<const float4*>(Wb + (rs * mul + ((k < MT && m < mul) ? m : 0)) * HA);
+                            }
+#pragma unroll 5
                             for (int c4 = 0; c4 < a4; ++c4) {
                                 const float4 av = ap[c4];
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    const int m = mc + k * MC;
-                                    if (k < MT && m < mul) {
-                                        const float4 w = *reinterpret_cast<const float4*>(wb + m * HA + 4 * c4);
+                                    if (k < MT) {
+                                        const float4 w = wp[k][c4];
                                         acc[p][k] = fmaf(av.x, w.x, acc[p][k]);
                                         acc[p][k] = fmaf(av.y, w.y, acc[p][k]);
                                         acc[p][k] = fmaf(av.z, w.z, acc[p][k]);
@@ -366,10 +441,10 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
                         }
                     }
                 }
+                __syncthreads();  // stage `buf` may be refilled by the prefetch of group g+2
             }
             // ---- reduce over the row slots in fixed order and add into the output channels
-            __syncthreads();
-            float* part = As;  // [RS][NB][mul]
+            float* part = As;  // [RS][NB][mul]  (all stages are idle here)
 #pragma unroll
             for (int p = 0; p < MAX_PASS; ++p) {
                 const int itx = tid + p * TT;
@@ -415,7 +490,8 @@ int launch_accumulate(const cb_tp_conv_args* a, int items, cudaStream_t st) {
         cb_set_error("cb_tp_conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return CB_ERR_CUDA;
     }
-    tp_accumulate_kernel<C><<<items, C::THREADS, smem, st>>>(*a);
+    const int grid = items < CB_NUM_SMS * 4 ? items : CB_NUM_SMS * 4;  // persistent CTAs, items strided across them
+    tp_accumulate_kernel<C><<<grid, C::THREADS, smem, st>>>(*a, items);
     CB_CHECK_LAUNCH("cb_tp_conv_forward(accumulate)");
     return CB_OK;
 }
@@ -474,7 +550,7 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
     }
     // transform + epilogue
     const int HA = H + PADC;
-    const size_t smem = sizeof(float) * ((size_t)MAX_RS * NB * HA + (size_t)MAX_WROWS * HA + (size_t)NB * a->d_out);
+    const size_t smem = sizeof(float) * (2 * (size_t)MAX_RS * NB * HA + 2 * (size_t)MAX_WROWS * HA + (size_t)NB * a->d_out);
     CB_CHECK_ARG(smem <= 110 * 1024, "cb_tp_conv_forward: transform kernel needs %zu B of shared memory", smem);
     cudaError_t e = cudaFuncSetAttribute(tp_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

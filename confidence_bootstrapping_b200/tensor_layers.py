@@ -90,7 +90,7 @@ class _DeviceProgram:
         self.rows = torch.from_numpy(prog.rows.view(np.uint8).copy()).to(device)
         self.terms = torch.from_numpy(prog.terms.view(np.uint8).copy()).to(device)
         self.runs = torch.from_numpy(prog.runs.view(np.uint8).copy()).to(device)
-        assert int(prog.runs["mul"].max()) <= 64, "transform kernel stages at most 64 weight rows per row group"
+        assert int(prog.runs["mul"].max()) <= 32, "transform kernel stages at most 32 weight rows per row group"
 
 
 class TensorProductConvLayer(nn.Module):
