@@ -192,6 +192,7 @@ class TpTimer:
 def run_cb200(opts):
     import torch.distributed as dist
     from confidence_bootstrapping_b200 import _lib
+    from confidence_bootstrapping_b200 import dist as cbdist
     from confidence_bootstrapping_b200.configs import confidence_model_args, score_model_args
     from confidence_bootstrapping_b200.data import Batch
     from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule, t_to_sigma
@@ -248,7 +249,12 @@ def run_cb200(opts):
                 fbatch["ligand"].pos = pos
                 fb = crop_beyond(fbatch, conf_args.crop_beyond, True) if conf_args.crop_beyond is not None else fbatch
                 set_time(fb, 0, 0, 0, 0, fb.num_graphs, True, False, dev)
-                conf_model(fb)
+                conf = conf_model(fb)[0]
+            else:
+                conf = None
+            if world > 1:
+                # the only collective of the path: final poses + confidences of every rank's complex
+                cbdist.gather_results([rank], [pos.view(SAMPLES, -1, 3)], [conf], world, device=dev)
         e.record()
         return s, e
 

@@ -1,0 +1,108 @@
+"""Multi-GPU sampling: shard the complex list across ranks, gather poses + confidences once at the end.
+
+The reference has no distributed backend: its only multi-GPU construct is PyG
+DataParallel for training.  The sampling path is embarrassingly parallel over (complex x sample)
+(utils/sampling.py:89-233 never mixes graphs), so the B200 design is one process per GPU
+(torch.distributed, NCCL over NVLink), the complex list partitioned longest-processing-time-first,
+all samples of a complex kept on one rank (they share the ligand topology, the cached receptor
+embedding and the K4 launch), NO collective inside the sampling loop, and a single variable-length
+all-gather of final ligand coordinates and confidences.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def estimate_cost(n_lig: int, n_rec: int, n_samples: int, rec_neighbors: int = 24) -> float:
+    """Edge-layers per step ~ samples * (cross edges + receptor edges)."""
+    return float(n_samples) * (n_lig * n_rec + rec_neighbors * n_rec)
+
+
+def partition_lpt(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Longest-processing-time-first: heaviest complex to the least loaded rank.  Deterministic
+    (ties broken by index), identical on every rank, so no communication is needed to agree on it."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * world_size
+    parts: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        parts[r].append(i)
+        loads[r] += costs[i]
+    for p in parts:
+        p.sort()
+    return parts
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def gather_results(local_ids: Sequence[int], poses: Sequence[torch.Tensor], confidences: Sequence[Optional[torch.Tensor]],
+                   n_total: int, device=None) -> Tuple[List[Optional[torch.Tensor]], List[Optional[torch.Tensor]]]:
+    """All-gather per-complex results.
+
+    local_ids[k] is the global index of the k-th local complex, poses[k] its [S, N_lig, 3] float32 final
+    coordinates, confidences[k] its [S] confidences (or None).  Every rank returns the full lists
+    (index = global complex id).  Payload is KB-MB: one padded all_gather of a flat float buffer plus
+    one of the int64 layout table; NCCL on GPUs, gloo for the CPU tests."""
+    rank, world = _world()
+    if world == 1:
+        out_p: List[Optional[torch.Tensor]] = [None] * n_total
+        out_c: List[Optional[torch.Tensor]] = [None] * n_total
+        for i, p, c in zip(local_ids, poses, confidences):
+            out_p[i], out_c[i] = p, c
+        return out_p, out_c
+    if device is None:
+        device = poses[0].device if len(poses) else torch.device("cpu")
+    # layout rows: (global id, S, N, has_conf)
+    meta = torch.tensor([[i, p.shape[0], p.shape[1], int(c is not None)] for i, p, c in zip(local_ids, poses, confidences)],
+                        dtype=torch.int64, device=device).reshape(-1, 4)
+    flat = [p.reshape(-1).float() for p in poses] + [c.reshape(-1).float() for c in confidences if c is not None]
+    payload = torch.cat(flat) if flat else torch.zeros(0, device=device)
+    sizes = torch.tensor([meta.shape[0], payload.numel()], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    max_meta = max(int(s[0]) for s in all_sizes)
+    max_pay = max(int(s[1]) for s in all_sizes)
+    meta_pad = torch.zeros((max(max_meta, 1), 4), dtype=torch.int64, device=device)
+    meta_pad[: meta.shape[0]] = meta
+    pay_pad = torch.zeros(max(max_pay, 1), dtype=torch.float32, device=device)
+    pay_pad[: payload.numel()] = payload
+    metas = [torch.zeros_like(meta_pad) for _ in range(world)]
+    pays = [torch.zeros_like(pay_pad) for _ in range(world)]
+    dist.all_gather(metas, meta_pad)
+    dist.all_gather(pays, pay_pad)
+    out_p = [None] * n_total
+    out_c = [None] * n_total
+    for r in range(world):
+        n_meta = int(all_sizes[r][0])
+        rows = metas[r][:n_meta].tolist()
+        off = 0
+        for (i, S, N, _) in rows:
+            out_p[i] = pays[r][off: off + S * N * 3].reshape(S, N, 3)
+            off += S * N * 3
+        for (i, S, N, has_c) in rows:
+            if has_c:
+                out_c[i] = pays[r][off: off + S]
+                off += S
+    return out_p, out_c
+
+
+def sample_complexes(complexes: Sequence, n_samples: int, sample_fn, costs: Optional[Sequence[float]] = None, device=None):
+    """Shard `complexes` over the ranks, run `sample_fn(complex, n_samples) -> (poses [S,N,3], conf [S] or None)`
+    on the local shard, and all-gather.  Returns (poses_per_complex, conf_per_complex) on every rank."""
+    rank, world = _world()
+    if costs is None:
+        costs = [estimate_cost(int(c["ligand"].num_nodes), int(c["receptor"].num_nodes), n_samples) for c in complexes]
+    mine = partition_lpt(costs, world)[rank]
+    poses, confs = [], []
+    for i in mine:
+        p, c = sample_fn(complexes[i], n_samples)
+        poses.append(p)
+        confs.append(c)
+    return gather_results(mine, poses, confs, len(complexes), device=device)
