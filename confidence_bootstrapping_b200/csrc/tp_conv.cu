@@ -290,6 +290,310 @@ tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ (a')
+// Tensor-core variant of the accumulate kernel: A[R x (H+1)] += F^T[R x K] . H~[K x (H+1)] per chunk of
+// K = 16 edges as tcgen05.mma.kind::tf32 with the accumulator in TMEM.  fp32 accuracy is kept with the
+// 3xTF32 split (x = hi + lo, hi = top 19 bits; D += Fhi.Hhi + Fhi.Hlo + Flo.Hhi, error ~2^-21).  The
+// constant-1 column of H~ makes column H of the accumulator the sum of f (bias term of the second Linear).
+// CUDA cores only produce the two operand tiles (CG products, hidden layer of the radial MLP) into shared
+// memory in the no-swizzle K-major core-matrix layout; one thread issues the MMAs; the tile is read back
+// once per (node, slot) with tcgen05.ld and written to the workspace.  256 threads, 2 CTAs per SM
+// (256 TMEM columns each).
+namespace tc {
+
+constexpr int KC = 16;          // edges per chunk = 2 MMA k-steps of 8
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 256;
+constexpr int LBO = 128;        // bytes between the two 16-byte K-chunks of a k-step (adjacent core matrices)
+constexpr int SBO = (KC / 4) * 128;  // bytes between 8-row groups
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version(1)<<46
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 26); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+        if (ok) return;
+    }
+    __trap();  // never hang the GPU: a lost MMA completion aborts the kernel instead
+}
+
+// byte offset of element (row, k) inside an operand tile
+__device__ __forceinline__ int tile_off(int row, int k) { return (row >> 3) * SBO + (k >> 2) * LBO + (row & 7) * 16 + (k & 3) * 4; }
+
+struct Layout {
+    int rows, terms, w1e, hbase, cols, xs, shs, es, ps, fhi, flo, hhi, hlo, total;  // byte offsets
+    int nep, dxp, npad, mtiles;
+};
+
+__host__ __device__ inline Layout make_layout(int n_rows, int n_terms, int ne, int d_in, int S, int H) {
+    Layout L;
+    auto al = [](int v, int a) { return (v + a - 1) / a * a; };
+    L.nep = ne + 4;
+    L.dxp = d_in | 1;
+    L.npad = al(H + 1, 16);
+    L.mtiles = (n_rows + 127) / 128;
+    int o = 0;
+    L.fhi = o;   o += L.mtiles * 16 * SBO;
+    L.flo = o;   o += L.mtiles * 16 * SBO;
+    L.hhi = o;   o += (L.npad / 8) * SBO;
+    L.hlo = o;   o += (L.npad / 8) * SBO;
+    L.rows = o;  o += al(n_rows * 32, 16);
+    L.terms = o; o += al(n_terms * 8, 16);
+    L.w1e = o;   o += al(H * L.nep * 4, 16);
+    L.hbase = o; o += al(H * 4, 16);
+    L.cols = o;  o += al(KC * 4, 16);
+    L.xs = o;    o += al(KC * L.dxp * 4, 16);
+    L.shs = o;   o += al(KC * S * 4, 16);
+    L.es = o;    o += al(KC * ne * 4, 16);
+    L.ps = o;    o += al(KC * H * 4, 16);
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    const int H = a.H, ne = a.ne, S = a.S, d_in = a.d_in, n_rows = a.n_rows;
+    const Layout L = make_layout(n_rows, a.n_terms, ne, d_in, S, H);
+    const int nep = L.nep, dxp = L.dxp, NP = L.npad, MT = L.mtiles, HA = H + PADC;
+    unsigned char* Fhi = smraw + L.fhi;
+    unsigned char* Flo = smraw + L.flo;
+    unsigned char* Hhi = smraw + L.hhi;
+    unsigned char* Hlo = smraw + L.hlo;
+    cb_tp_row* rows_s = reinterpret_cast<cb_tp_row*>(smraw + L.rows);
+    cb_tp_term* terms_s = reinterpret_cast<cb_tp_term*>(smraw + L.terms);
+    float* W1e_s = reinterpret_cast<float*>(smraw + L.w1e);
+    float* hbase = reinterpret_cast<float*>(smraw + L.hbase);
+    int* cols_s = reinterpret_cast<int*>(smraw + L.cols);
+    float* xs = reinterpret_cast<float*>(smraw + L.xs);
+    float* shs = reinterpret_cast<float*>(smraw + L.shs);
+    float* es = reinterpret_cast<float*>(smraw + L.es);
+    float* Ps = reinterpret_cast<float*>(smraw + L.ps);
+    __shared__ SlotTable st;
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- once per persistent CTA
+    if (tid == 0) {
+        build_slots(a, st);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    {
+        const int* src = reinterpret_cast<const int*>(a.rows);
+        int* dst = reinterpret_cast<int*>(rows_s);
+        for (int i = tid; i < n_rows * 8; i += THREADS) dst[i] = src[i];
+        const int2* tsrc = reinterpret_cast<const int2*>(a.terms);
+        int2* tdst = reinterpret_cast<int2*>(terms_s);
+        for (int i = tid; i < a.n_terms; i += THREADS) tdst[i] = tsrc[i];
+        // operand tiles start as zeros: padding rows (r >= n_rows, q > H) are never written again
+        for (int i = tid; i < (L.rows - L.fhi) / 16; i += THREADS) reinterpret_cast<float4*>(smraw + L.fhi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t commits = 0, waited = 0;   // block-uniform bookkeeping of the MMA barrier phases
+    int staged_slot = -1;
+    int q = 0;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        while (q + 1 < st.n_slots && item >= st.item_off[q + 1]) ++q;
+        const int node = st.lo[q] + (item - st.item_off[q]);
+        const int seg0 = st.first_seg[q], nseg = st.n_segs[q];
+        int deg = 0;
+        for (int s = seg0; s < seg0 + nseg; ++s) {
+            const cb_tp_segment& sg = a.segs[s];
+            deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
+        }
+        if (deg == 0) continue;  // block-uniform
+
+        const cb_tp_segment& s0 = a.segs[seg0];
+        __syncthreads();  // previous item fully retired (epilogue done, staging buffers free)
+        if (staged_slot != q) {
+            for (int i = tid; i < H * (ne / 4); i += THREADS) {
+                const int qq = i / (ne / 4), c4 = i - qq * (ne / 4);
+                *reinterpret_cast<float4*>(W1e_s + qq * nep + 4 * c4) =
+                    __ldg(reinterpret_cast<const float4*>(s0.W1e + (size_t)qq * s0.ldw1) + c4);
+            }
+            staged_slot = q;
+            __syncthreads();
+        }
+        const int graph = a.agg_graph ? a.agg_graph[node] : 0;
+        for (int qq = tid; qq < H; qq += THREADS) {
+            float v = s0.b1[qq];
+            if (s0.P_agg) v += s0.P_agg[(size_t)node * s0.ldp_agg + qq];
+            if (s0.e_post) {
+                const float* ep = s0.e_post + (size_t)graph * ne;
+                for (int c = 0; c < ne; ++c) v = fmaf(W1e_s[qq * nep + c], ep[c], v);
+            }
+            hbase[qq] = v;
+        }
+        bool first_mma = true;
+
+        for (int s = seg0; s < seg0 + nseg; ++s) {
+            const cb_tp_segment& sg = a.segs[s];
+            const int e0 = sg.rowptr[node - sg.n0], e1 = sg.rowptr[node - sg.n0 + 1];
+            for (int base = e0; base < e1; base += KC) {
+                const int n = min(KC, e1 - base);
+                // ---- gather raw operands (overlaps the MMAs of the previous chunk)
+                if (tid < n) cols_s[tid] = sg.col[base + tid] + sg.col_off;
+                __syncthreads();
+                for (int e = warp; e < n; e += THREADS / 32) {
+                    const float* xr = a.x + (size_t)cols_s[e] * d_in;
+                    for (int k = lane; k < d_in; k += 32) xs[e * dxp + k] = __ldg(xr + k);
+                    if (sg.P_nbr) {
+                        const float* pr = sg.P_nbr + (size_t)cols_s[e] * sg.ldp_nbr;
+                        for (int k = lane; k < H; k += 32) Ps[e * H + k] = __ldg(pr + k);
+                    }
+                }
+                for (int i = tid; i < n * S; i += THREADS) shs[i] = __ldg(sg.sh + (size_t)base * S + i);
+                for (int i = tid; i < n * (ne / 4); i += THREADS)
+                    reinterpret_cast<float4*>(es)[i] = __ldg(reinterpret_cast<const float4*>(sg.e_attr + (size_t)base * ne) + i);
+                // the operand tiles are free once the previous chunk's MMAs have completed
+                if (waited < commits) {
+                    mbar_wait(&mma_bar, waited & 1);
+                    ++waited;
+                }
+                __syncthreads();
+                // ---- F^T tile: row r = f-row, column = edge; hi/lo TF32 split
+                for (int r = tid; r < n_rows; r += THREADS) {
+                    const int tb = rows_s[r].term_begin, te = rows_s[r].term_end;
+                    for (int e = 0; e < KC; ++e) {
+                        float v = 0.0f;
+                        if (e < n) {
+                            const float* xe = xs + e * dxp;
+                            const float* se = shs + e * S;
+                            for (int t = tb; t < te; ++t) {
+                                const cb_tp_term tm = terms_s[t];
+                                v = fmaf(tm.coef * xe[tm.x_idx], se[tm.sh_idx], v);
+                            }
+                        }
+                        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                        const int off = tile_off(r, e);
+                        *reinterpret_cast<float*>(Fhi + off) = hi;
+                        *reinterpret_cast<float*>(Flo + off) = v - hi;
+                    }
+                }
+                // ---- H~ tile: row q = hidden unit (row H = constant 1), column = edge
+                for (int i = tid; i < (H + 1) * 2; i += THREADS) {
+                    const int qq = i >> 1, half = i & 1;
+                    const float4* w4 = reinterpret_cast<const float4*>(W1e_s + qq * nep);
+                    for (int e = half * (KC / 2); e < (half + 1) * (KC / 2); ++e) {
+                        float v = 0.0f;
+                        if (e < n) {
+                            if (qq == H) {
+                                v = 1.0f;
+                            } else {
+                                v = hbase[qq];
+                                if (sg.P_nbr) v += Ps[e * H + qq];
+                                const float4* e4 = reinterpret_cast<const float4*>(es + e * ne);
+                                for (int c = 0; c < ne / 4; ++c) {
+                                    const float4 w = w4[c], x4 = e4[c];
+                                    v = fmaf(w.x, x4.x, v);
+                                    v = fmaf(w.y, x4.y, v);
+                                    v = fmaf(w.z, x4.z, v);
+                                    v = fmaf(w.w, x4.w, v);
+                                }
+                                v = fmaxf(v, 0.0f);
+                            }
+                        }
+                        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                        const int off = tile_off(qq, e);
+                        *reinterpret_cast<float*>(Hhi + off) = hi;
+                        *reinterpret_cast<float*>(Hlo + off) = v - hi;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+                __syncthreads();
+                // ---- one thread issues the MMAs of this chunk and commits them to the barrier
+                if (tid == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int ksteps = (n + 7) >> 3;
+                    const uint32_t fhi = smem_u32(Fhi), flo = smem_u32(Flo), hhi = smem_u32(Hhi), hlo = smem_u32(Hlo);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t d = tmem_base + (uint32_t)(mt * NP);
+                        uint32_t acc = first_mma ? 0u : 1u;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t ao = (uint32_t)(mt * 16 * SBO + ks * 2 * LBO), bo = (uint32_t)(ks * 2 * LBO);
+                            mma_tf32(d, make_desc(fhi + ao), make_desc(hhi + bo), idesc, acc);
+                            mma_tf32(d, make_desc(fhi + ao), make_desc(hlo + bo), idesc, 1u);
+                            mma_tf32(d, make_desc(flo + ao), make_desc(hhi + bo), idesc, 1u);
+                            acc = 1u;
+                        }
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
+                                 : "memory");
+                }
+                first_mma = false;
+                ++commits;
+            }
+        }
+        // ---- epilogue: wait for the last MMAs, read the tile back from TMEM, write it to the workspace
+        while (waited < commits) {
+            mbar_wait(&mma_bar, waited & 1);
+            ++waited;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* Aout = a.workspace + (size_t)item * n_rows * HA;
+        const int lg = warp & 3;                 // TMEM lane group this warp may access
+        for (int mt = warp >> 2; mt < MT; mt += THREADS / 128) {
+            const int r = mt * 128 + lg * 32 + lane;
+            for (int c0 = 0; c0 < NP; c0 += 16) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * NP + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (r < n_rows) {
+                    float* dst = Aout + (size_t)r * HA + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        if (c0 + j < HA)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+}  // namespace tc
+
 // ------------------------------------------------------------------------------------------ (b)
 constexpr int NB = 32;        // nodes per CTA
 constexpr int TT = 256;       // threads
@@ -538,6 +842,23 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
                      "cb_tp_conv_forward: workspace too small (%lld floats for %lld accumulators)",
                      (long long)a->workspace_floats, (long long)items);
         int rc;
+        if (a->accum_mode == 2) {
+            CB_CHECK_ARG(R <= 384 && ((R + 127) / 128) * ((H + 1 + 15) / 16 * 16) <= tc::TMEM_COLS,
+                         "cb_tp_conv_forward: tcgen05 accumulate supports rows<=384 and tiles within 256 TMEM columns (rows=%d H=%d)", R, H);
+            const tc::Layout L = tc::make_layout(R, a->n_terms, a->ne, a->d_in, a->S, H);
+            // at least 80 KB so that never more than 2 CTAs (2 x 256 TMEM columns) share an SM
+            const size_t smem = (size_t)(L.total > 80 * 1024 ? L.total : 80 * 1024);
+            CB_CHECK_ARG(smem <= 112 * 1024, "cb_tp_conv_forward: tcgen05 accumulate needs %zu B of shared memory", smem);
+            cudaError_t e = cudaFuncSetAttribute(tc::tp_accumulate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                cb_set_error("cb_tp_conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                return CB_ERR_CUDA;
+            }
+            const int grid = items < CB_NUM_SMS * 2 ? (int)items : CB_NUM_SMS * 2;
+            tc::tp_accumulate_tc_kernel<<<grid, tc::THREADS, smem, st>>>(*a, (int)items);
+            CB_CHECK_LAUNCH("cb_tp_conv_forward(accumulate, tcgen05)");
+            rc = CB_OK;
+        } else
         if (H <= 64 && R <= 256) rc = launch_accumulate<Cfg<64, 8, 4, 8>>(a, (int)items, st);
         else if (H <= 96 && R <= 256) rc = launch_accumulate<Cfg<64, 8, 4, 12>>(a, (int)items, st);
         else if (H <= 80 && R <= 320) rc = launch_accumulate<Cfg<80, 4, 4, 20>>(a, (int)items, st);

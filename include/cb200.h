@@ -169,6 +169,8 @@ typedef struct {
      * aggregation nodes [node_begin, node_end) and needs cb_tp_conv_items(a) * n_rows * (H+4) floats   */
     float* workspace; int64_t workspace_floats;
     int32_t node_begin, node_end;
+    int32_t accum_mode;     /* accumulate kernel: 1 = fp32 FFMA register tiles, 2 = tcgen05 3xTF32 with TMEM accumulator */
+    int32_t pad_;
 } cb_tp_conv_args;
 /* number of (node, slot) accumulators the call will use (host arithmetic only) */
 int64_t cb_tp_conv_items(const cb_tp_conv_args* a);

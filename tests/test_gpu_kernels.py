@@ -215,3 +215,40 @@ def test_sde_step_vs_reference_golden():
     want = osamp.modify_conformer_batch(pos0, bb, tr, rot, tor, torch.from_numpy(mr))
     got = modify_conformer_batch(pos0.cuda(), bb.to("cuda"), tr.cuda(), rot.cuda(), tor.cuda(), mr)
     assert rmsd(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("in_ir,sh_l,out_ir,faster,groups,nef", [
+    (SEQ[3], 1, SEQ[3], True, 4, 96), (SEQ[0], 1, SEQ[1], True, 1, 96), (CONF[3], 2, CONF[3], False, 9, 72),
+    (SEQ[3], 1, "2x1o + 2x1e", False, 1, 64)])
+def test_tp_conv_layer_tcgen05_accumulate(in_ir, sh_l, out_ir, faster, groups, nef):
+    """K3 with the tcgen05 (3xTF32, TMEM accumulator) accumulate kernel: same 1e-5 relative bar as the fp32 path."""
+    from confidence_bootstrapping_b200 import tensor_layers
+    from confidence_bootstrapping_b200.tensor_layers import TensorProductConvLayer
+    from helpers import randomize_norm_stats
+    torch.manual_seed(0)
+    sh_ir = "1x0e + 1x1o" if sh_l == 1 else "1x0e + 1x1o + 1x2e"
+    residual = out_ir != "2x1o + 2x1e"
+    layer = TensorProductConvLayer(in_ir, sh_ir, out_ir, nef, residual=residual, batch_norm=True, hidden_features=nef,
+                                   faster=faster, edge_groups=groups)
+    randomize_norm_stats(layer, seed=1)
+    layer.eval()
+    n_nodes, n_edges = 150, 3000
+    x = torch.randn(n_nodes, o3.Irreps(in_ir).dim)
+    n_out = 9 if not residual else n_nodes
+    ei = _random_graph(5, n_nodes, n_edges, n_out)
+    sh = o3.spherical_harmonics(list(range(sh_l + 1)), torch.randn(n_edges, 3), True, "component")
+    ea = torch.randn(n_edges, nef)
+    bounds = np.linspace(0, n_edges, groups + 1).astype(int)
+    ea_list = [ea[bounds[g]:bounds[g + 1]] for g in range(groups)] if groups > 1 else ea
+    sd = {"x." + k: v.clone() for k, v in layer.state_dict().items()}
+    with torch.no_grad():
+        want = om.tp_conv_layer(sd, "x", in_ir, o3.Irreps(sh_ir), out_ir, faster, groups, residual, True, x, ei, ea_list, sh, out_nodes=n_out)
+        layer = layer.cuda()
+        old = tensor_layers.ACCUM_MODE
+        tensor_layers.ACCUM_MODE = 2
+        try:
+            got = layer(x.cuda(), ei.cuda(), [e.cuda() for e in ea_list] if groups > 1 else ea.cuda(), sh.cuda(), out_nodes=n_out)
+            torch.cuda.synchronize()
+        finally:
+            tensor_layers.ACCUM_MODE = old
+    assert rel_err(got, want) < 1e-5
