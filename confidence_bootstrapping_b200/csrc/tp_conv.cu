@@ -324,6 +324,7 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (int spin = 0; spin < (1 << 26); ++spin) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
@@ -407,11 +408,14 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     {
         const int* src = reinterpret_cast<const int*>(a.rows);
         int* dst = reinterpret_cast<int*>(rows_s);
+#pragma unroll 1
         for (int i = tid; i < n_rows * 8; i += THREADS) dst[i] = src[i];
         const int2* tsrc = reinterpret_cast<const int2*>(a.terms);
         int2* tdst = reinterpret_cast<int2*>(terms_s);
+#pragma unroll 1
         for (int i = tid; i < a.n_terms; i += THREADS) tdst[i] = tsrc[i];
         // operand tiles start as zeros: padding rows (r >= n_rows, q > H) are never written again
+#pragma unroll 1
         for (int i = tid; i < (L.rows - L.fhi) / 16; i += THREADS) reinterpret_cast<float4*>(smraw + L.fhi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -422,12 +426,31 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     uint32_t commits = 0, waited = 0;   // block-uniform bookkeeping of the MMA barrier phases
     int staged_slot = -1;
     int q = 0;
+    // terms of the thread's (first) f-row live in registers; rows beyond THREADS use the generic loop
+    constexpr int MAXT = 4;
+    int tb0 = 0, te0 = 0, t_xi[MAXT], t_si[MAXT];
+    float t_cf[MAXT];
+    if (tid < n_rows) {
+        tb0 = rows_s[tid].term_begin;
+        te0 = rows_s[tid].term_end;
+    }
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+        const bool on = tid < n_rows && tb0 + t < te0;
+        const cb_tp_term tm = on ? terms_s[tb0 + t] : cb_tp_term{0, 0, 0.0f};
+        t_xi[t] = tm.x_idx;
+        t_si[t] = tm.sh_idx;
+        t_cf[t] = on ? tm.coef : 0.0f;
+    }
+    // MMA descriptors are CTA constants
+    const uint32_t fhi_a = smem_u32(Fhi), flo_a = smem_u32(Flo), hhi_a = smem_u32(Hhi), hlo_a = smem_u32(Hlo);
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         while (q + 1 < st.n_slots && item >= st.item_off[q + 1]) ++q;
         const int node = st.lo[q] + (item - st.item_off[q]);
         const int seg0 = st.first_seg[q], nseg = st.n_segs[q];
         int deg = 0;
+#pragma unroll 1
         for (int s = seg0; s < seg0 + nseg; ++s) {
             const cb_tp_segment& sg = a.segs[s];
             deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
@@ -437,6 +460,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         const cb_tp_segment& s0 = a.segs[seg0];
         __syncthreads();  // previous item fully retired (epilogue done, staging buffers free)
         if (staged_slot != q) {
+#pragma unroll 1
             for (int i = tid; i < H * (ne / 4); i += THREADS) {
                 const int qq = i / (ne / 4), c4 = i - qq * (ne / 4);
                 *reinterpret_cast<float4*>(W1e_s + qq * nep + 4 * c4) =
@@ -446,34 +470,43 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             __syncthreads();
         }
         const int graph = a.agg_graph ? a.agg_graph[node] : 0;
+#pragma unroll 1
         for (int qq = tid; qq < H; qq += THREADS) {
             float v = s0.b1[qq];
             if (s0.P_agg) v += s0.P_agg[(size_t)node * s0.ldp_agg + qq];
             if (s0.e_post) {
                 const float* ep = s0.e_post + (size_t)graph * ne;
+#pragma unroll 4
                 for (int c = 0; c < ne; ++c) v = fmaf(W1e_s[qq * nep + c], ep[c], v);
             }
             hbase[qq] = v;
         }
         bool first_mma = true;
 
+#pragma unroll 1
         for (int s = seg0; s < seg0 + nseg; ++s) {
             const cb_tp_segment& sg = a.segs[s];
             const int e0 = sg.rowptr[node - sg.n0], e1 = sg.rowptr[node - sg.n0 + 1];
+#pragma unroll 1
             for (int base = e0; base < e1; base += KC) {
                 const int n = min(KC, e1 - base);
                 // ---- gather raw operands (overlaps the MMAs of the previous chunk)
                 if (tid < n) cols_s[tid] = sg.col[base + tid] + sg.col_off;
                 __syncthreads();
+#pragma unroll 1
                 for (int e = warp; e < n; e += THREADS / 32) {
                     const float* xr = a.x + (size_t)cols_s[e] * d_in;
+#pragma unroll 1
                     for (int k = lane; k < d_in; k += 32) xs[e * dxp + k] = __ldg(xr + k);
                     if (sg.P_nbr) {
                         const float* pr = sg.P_nbr + (size_t)cols_s[e] * sg.ldp_nbr;
+#pragma unroll 1
                         for (int k = lane; k < H; k += 32) Ps[e * H + k] = __ldg(pr + k);
                     }
                 }
+#pragma unroll 1
                 for (int i = tid; i < n * S; i += THREADS) shs[i] = __ldg(sg.sh + (size_t)base * S + i);
+#pragma unroll 1
                 for (int i = tid; i < n * (ne / 4); i += THREADS)
                     reinterpret_cast<float4*>(es)[i] = __ldg(reinterpret_cast<const float4*>(sg.e_attr + (size_t)base * ne) + i);
                 // the operand tiles are free once the previous chunk's MMAs have completed
@@ -482,52 +515,116 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     ++waited;
                 }
                 __syncthreads();
-                // ---- F^T tile: row r = f-row, column = edge; hi/lo TF32 split
-                for (int r = tid; r < n_rows; r += THREADS) {
-                    const int tb = rows_s[r].term_begin, te = rows_s[r].term_end;
-                    for (int e = 0; e < KC; ++e) {
-                        float v = 0.0f;
-                        if (e < n) {
+                // ---- F^T tile: row r = f-row, column = edge; hi/lo TF32 split.  Loops stay rolled on purpose:
+                // the kernel must fit the 32 KB instruction cache (an unrolled build stalled on instruction fetch).
+                const int nq = 2 * ((n + 7) >> 3);   // 4-edge groups covered by the MMA k-steps of this chunk
+                if (tid < n_rows) {
+                    const int rbase = (tid >> 3) * SBO + (tid & 7) * 16;
+#pragma unroll 1
+                    for (int e4 = 0; e4 < nq; ++e4) {
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = min(4 * e4 + j, n - 1);          // clamp: edges >= n are zeroed below
                             const float* xe = xs + e * dxp;
                             const float* se = shs + e * S;
-                            for (int t = tb; t < te; ++t) {
-                                const cb_tp_term tm = terms_s[t];
-                                v = fmaf(tm.coef * xe[tm.x_idx], se[tm.sh_idx], v);
+                            float acc = 0.0f;
+#pragma unroll
+                            for (int t = 0; t < MAXT; ++t) acc = fmaf(t_cf[t] * xe[t_xi[t]], se[t_si[t]], acc);
+                            v[j] = (4 * e4 + j < n) ? acc : 0.0f;
+                        }
+                        if (te0 - tb0 > MAXT) {   // rare long rows: finish from the shared-memory term table
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int e = 4 * e4 + j;
+                                if (e < n)
+#pragma unroll 1
+                                    for (int t = tb0 + MAXT; t < te0; ++t) {
+                                        const cb_tp_term tm = terms_s[t];
+                                        v[j] = fmaf(tm.coef * xs[e * dxp + tm.x_idx], shs[e * S + tm.sh_idx], v[j]);
+                                    }
                             }
                         }
-                        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-                        const int off = tile_off(r, e);
-                        *reinterpret_cast<float*>(Fhi + off) = hi;
-                        *reinterpret_cast<float*>(Flo + off) = v - hi;
+                        float4 hi, lo;
+                        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
+                        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
+                        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
+                        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
+                        lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+                        *reinterpret_cast<float4*>(Fhi + rbase + e4 * LBO) = hi;   // 4 consecutive edges = one 16-byte core-matrix row
+                        *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
+                    }
+                }
+#pragma unroll 1
+                for (int r = tid + THREADS; r < n_rows; r += THREADS) {   // rows beyond the first 256 (lmax-2 layers)
+                    const int tb = rows_s[r].term_begin, te = rows_s[r].term_end;
+                    const int rbase = (r >> 3) * SBO + (r & 7) * 16;
+#pragma unroll 1
+                    for (int e4 = 0; e4 < nq; ++e4) {
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = 4 * e4 + j;
+                            float acc = 0.0f;
+                            if (e < n)
+#pragma unroll 1
+                                for (int t = tb; t < te; ++t) {
+                                    const cb_tp_term tm = terms_s[t];
+                                    acc = fmaf(tm.coef * xs[e * dxp + tm.x_idx], shs[e * S + tm.sh_idx], acc);
+                                }
+                            v[j] = acc;
+                        }
+                        float4 hi, lo;
+                        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
+                        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
+                        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
+                        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
+                        lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+                        *reinterpret_cast<float4*>(Fhi + rbase + e4 * LBO) = hi;
+                        *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
                     }
                 }
                 // ---- H~ tile: row q = hidden unit (row H = constant 1), column = edge
+#pragma unroll 1
                 for (int i = tid; i < (H + 1) * 2; i += THREADS) {
                     const int qq = i >> 1, half = i & 1;
                     const float4* w4 = reinterpret_cast<const float4*>(W1e_s + qq * nep);
-                    for (int e = half * (KC / 2); e < (half + 1) * (KC / 2); ++e) {
-                        float v = 0.0f;
-                        if (e < n) {
-                            if (qq == H) {
-                                v = 1.0f;
-                            } else {
-                                v = hbase[qq];
-                                if (sg.P_nbr) v += Ps[e * H + qq];
-                                const float4* e4 = reinterpret_cast<const float4*>(es + e * ne);
-                                for (int c = 0; c < ne / 4; ++c) {
-                                    const float4 w = w4[c], x4 = e4[c];
-                                    v = fmaf(w.x, x4.x, v);
-                                    v = fmaf(w.y, x4.y, v);
-                                    v = fmaf(w.z, x4.z, v);
-                                    v = fmaf(w.w, x4.w, v);
+                    const int rbase = (qq >> 3) * SBO + (qq & 7) * 16;
+#pragma unroll 1
+                    for (int e4 = half; e4 < nq; e4 += 2) {
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = 4 * e4 + j;
+                            float acc = 0.0f;
+                            if (e < n) {
+                                if (qq == H) {
+                                    acc = 1.0f;
+                                } else {
+                                    acc = hbase[qq];
+                                    if (sg.P_nbr) acc += Ps[e * H + qq];
+                                    const float4* ev = reinterpret_cast<const float4*>(es + e * ne);
+#pragma unroll 2
+                                    for (int c = 0; c < ne / 4; ++c) {
+                                        const float4 w = w4[c], x4 = ev[c];
+                                        acc = fmaf(w.x, x4.x, acc);
+                                        acc = fmaf(w.y, x4.y, acc);
+                                        acc = fmaf(w.z, x4.z, acc);
+                                        acc = fmaf(w.w, x4.w, acc);
+                                    }
+                                    acc = fmaxf(acc, 0.0f);
                                 }
-                                v = fmaxf(v, 0.0f);
                             }
+                            v[j] = acc;
                         }
-                        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-                        const int off = tile_off(qq, e);
-                        *reinterpret_cast<float*>(Hhi + off) = hi;
-                        *reinterpret_cast<float*>(Hlo + off) = v - hi;
+                        float4 hi, lo;
+                        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
+                        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
+                        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
+                        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
+                        lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+                        *reinterpret_cast<float4*>(Hhi + rbase + e4 * LBO) = hi;
+                        *reinterpret_cast<float4*>(Hlo + rbase + e4 * LBO) = lo;
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
@@ -536,10 +633,12 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 if (tid == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const int ksteps = (n + 7) >> 3;
-                    const uint32_t fhi = smem_u32(Fhi), flo = smem_u32(Flo), hhi = smem_u32(Hhi), hlo = smem_u32(Hlo);
+                    const uint32_t fhi = fhi_a, flo = flo_a, hhi = hhi_a, hlo = hlo_a;
+#pragma unroll 1
                     for (int mt = 0; mt < MT; ++mt) {
                         const uint32_t d = tmem_base + (uint32_t)(mt * NP);
                         uint32_t acc = first_mma ? 0u : 1u;
+#pragma unroll 1
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint32_t ao = (uint32_t)(mt * 16 * SBO + ks * 2 * LBO), bo = (uint32_t)(ks * 2 * LBO);
                             mma_tf32(d, make_desc(fhi + ao), make_desc(hhi + bo), idesc, acc);
@@ -563,21 +662,29 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* Aout = a.workspace + (size_t)item * n_rows * HA;
         const int lg = warp & 3;                 // TMEM lane group this warp may access
+#pragma unroll 1
         for (int mt = warp >> 2; mt < MT; mt += THREADS / 128) {
             const int r = mt * 128 + lg * 32 + lane;
-            for (int c0 = 0; c0 < NP; c0 += 16) {
-                uint32_t v[16];
+#pragma unroll 1
+            for (int c0 = 0; c0 < NP; c0 += 32) {   // NP is a multiple of 16; a trailing half chunk reads 16 spare columns
+                uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * NP + c0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
                       "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                     : "r"(taddr));
+                if (c0 + 16 < NP)
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                        : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr + 16u));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (r < n_rows) {
                     float* dst = Aout + (size_t)r * HA + c0;
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
+                    for (int j = 0; j < 32; j += 4)
                         if (c0 + j < HA)
                             *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));

@@ -22,8 +22,9 @@ from .irreps import (TPProgram, faster_tp_program, fctp_program, get_irrep_seq, 
                      parse_irreps, sh_irreps)
 
 ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
-# accumulate kernel of K3: 1 = fp32 FFMA register tiles, 2 = tcgen05 3xTF32 + TMEM accumulator
-ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "1"))
+# accumulate kernel of K3: 2 = tcgen05 3xTF32 UMMA + TMEM accumulator (default);
+# 1 = fp32 FFMA register tiles (kept for shapes outside the UMMA tile limits and for A/B measurements)
+ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "2"))
 WORKSPACE_BYTES = 6 << 30  # cap on the K3 accumulator workspace; larger layers are processed in node chunks
 
 
@@ -221,7 +222,9 @@ class TensorProductConvLayer(nn.Module):
         # workspace: one R x (H+4) accumulator per (node, slot); process the nodes in chunks if it would be huge
         per_item = P.n_rows * (H + 4)
         a.node_begin, a.node_end = 0, n_out
-        a.accum_mode = ACCUM_MODE
+        np_cols = -(-(H + 1) // 16) * 16
+        tc_ok = P.n_rows <= 384 and -(-P.n_rows // 128) * np_cols <= 256
+        a.accum_mode = ACCUM_MODE if tc_ok else 1
         items = _lib.tp_conv_items(a)
         max_items = max(1, WORKSPACE_BYTES // (4 * per_item))
         n_chunks = max(1, -(-items // max_items))
