@@ -348,7 +348,7 @@ __host__ __device__ inline Layout make_layout(int n_rows, int n_terms, int ne, i
     Layout L;
     auto al = [](int v, int a) { return (v + a - 1) / a * a; };
     L.nep = ne + 4;
-    L.dxp = d_in | 1;
+    L.dxp = d_in + (d_in & 1);   // even: rows are filled with 8-byte cp.async
     L.npad = al(H + 1, 16);
     L.mtiles = (n_rows + 127) / 128;
     int o = 0;
@@ -360,13 +360,29 @@ __host__ __device__ inline Layout make_layout(int n_rows, int n_terms, int ne, i
     L.terms = o; o += al(n_terms * 8, 16);
     L.w1e = o;   o += al(H * L.nep * 4, 16);
     L.hbase = o; o += al(H * 4, 16);
-    L.cols = o;  o += al(KC * 4, 16);
-    L.xs = o;    o += al(KC * L.dxp * 4, 16);
-    L.shs = o;   o += al(KC * S * 4, 16);
-    L.es = o;    o += al(KC * ne * 4, 16);
-    L.ps = o;    o += al(KC * H * 4, 16);
+    L.cols = o;  o += al(2 * KC * 4, 16);          // raw-operand staging is double buffered
+    L.xs = o;    o += al(2 * KC * L.dxp * 4, 16);
+    L.shs = o;   o += al(2 * KC * S * 4, 16);
+    L.es = o;    o += al(2 * KC * ne * 4, 16);
+    L.ps = o;    o += al(2 * KC * H * 4, 16);
     L.total = o;
     return L;
+}
+
+// One chunk of <= KC edges of one (node, slot) item; every thread tracks the same iterator.
+struct Chunk {
+    int item, q, node, seg, base, n;
+    bool valid, first, last;
+};
+
+__device__ __forceinline__ void cp_async_bytes8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_bytes4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_bytes16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
 }
 
 __global__ void __launch_bounds__(THREADS, 2)
@@ -383,16 +399,17 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     cb_tp_term* terms_s = reinterpret_cast<cb_tp_term*>(smraw + L.terms);
     float* W1e_s = reinterpret_cast<float*>(smraw + L.w1e);
     float* hbase = reinterpret_cast<float*>(smraw + L.hbase);
-    int* cols_s = reinterpret_cast<int*>(smraw + L.cols);
-    float* xs = reinterpret_cast<float*>(smraw + L.xs);
-    float* shs = reinterpret_cast<float*>(smraw + L.shs);
-    float* es = reinterpret_cast<float*>(smraw + L.es);
-    float* Ps = reinterpret_cast<float*>(smraw + L.ps);
     __shared__ SlotTable st;
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // double-buffered staging of the raw per-edge operands (filled by cp.async one chunk ahead)
+    auto cols_of = [&](int b) { return reinterpret_cast<int*>(smraw + L.cols) + b * KC; };
+    auto xs_of = [&](int b) { return reinterpret_cast<float*>(smraw + L.xs) + b * KC * dxp; };
+    auto shs_of = [&](int b) { return reinterpret_cast<float*>(smraw + L.shs) + b * KC * S; };
+    auto es_of = [&](int b) { return reinterpret_cast<float*>(smraw + L.es) + b * KC * ne; };
+    auto ps_of = [&](int b) { return reinterpret_cast<float*>(smraw + L.ps) + b * KC * H; };
 
     // ---- once per persistent CTA
     if (tid == 0) {
@@ -425,7 +442,6 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     uint32_t commits = 0, waited = 0;   // block-uniform bookkeeping of the MMA barrier phases
     int staged_slot = -1;
-    int q = 0;
     // terms of the thread's (first) f-row live in registers; rows beyond THREADS use the generic loop
     constexpr int MAXT = 4;
     int tb0 = 0, te0 = 0, t_xi[MAXT], t_si[MAXT];
@@ -442,257 +458,327 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         t_si[t] = tm.sh_idx;
         t_cf[t] = on ? tm.coef : 0.0f;
     }
-    // MMA descriptors are CTA constants
     const uint32_t fhi_a = smem_u32(Fhi), flo_a = smem_u32(Flo), hhi_a = smem_u32(Hhi), hlo_a = smem_u32(Hlo);
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        while (q + 1 < st.n_slots && item >= st.item_off[q + 1]) ++q;
-        const int node = st.lo[q] + (item - st.item_off[q]);
-        const int seg0 = st.first_seg[q], nseg = st.n_segs[q];
-        int deg = 0;
+    // ---- chunk iterator (block-uniform): items of this CTA in increasing order, their segments, KC edges at a time
+    auto seg_range = [&](int seg, int node, int& e0, int& e1) {
+        const cb_tp_segment& sg = a.segs[seg];
+        e0 = __ldg(sg.rowptr + (node - sg.n0));
+        e1 = __ldg(sg.rowptr + (node - sg.n0) + 1);
+    };
+    auto open_item = [&](Chunk& c, int item, int q) {
+        // first non-empty segment of the first non-empty item at or after `item`
+        c.valid = false;
 #pragma unroll 1
-        for (int s = seg0; s < seg0 + nseg; ++s) {
-            const cb_tp_segment& sg = a.segs[s];
-            deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
-        }
-        if (deg == 0) continue;  // block-uniform
-
-        const cb_tp_segment& s0 = a.segs[seg0];
-        __syncthreads();  // previous item fully retired (epilogue done, staging buffers free)
-        if (staged_slot != q) {
+        for (; item < n_items; item += gridDim.x) {
+            while (q + 1 < st.n_slots && item >= st.item_off[q + 1]) ++q;
+            const int node = st.lo[q] + (item - st.item_off[q]);
 #pragma unroll 1
-            for (int i = tid; i < H * (ne / 4); i += THREADS) {
-                const int qq = i / (ne / 4), c4 = i - qq * (ne / 4);
-                *reinterpret_cast<float4*>(W1e_s + qq * nep + 4 * c4) =
-                    __ldg(reinterpret_cast<const float4*>(s0.W1e + (size_t)qq * s0.ldw1) + c4);
+            for (int seg = st.first_seg[q]; seg < st.first_seg[q] + st.n_segs[q]; ++seg) {
+                int e0, e1;
+                seg_range(seg, node, e0, e1);
+                if (e1 > e0) {
+                    c.item = item; c.q = q; c.node = node; c.seg = seg; c.base = e0; c.n = min(KC, e1 - e0);
+                    c.valid = true; c.first = true;
+                    return e1;
+                }
             }
-            staged_slot = q;
-            __syncthreads();
         }
-        const int graph = a.agg_graph ? a.agg_graph[node] : 0;
+        return 0;
+    };
+    auto has_more = [&](const Chunk& c, int e1) {   // more edges of the same item after this chunk?
+        if (c.base + KC < e1) return true;
 #pragma unroll 1
-        for (int qq = tid; qq < H; qq += THREADS) {
-            float v = s0.b1[qq];
-            if (s0.P_agg) v += s0.P_agg[(size_t)node * s0.ldp_agg + qq];
-            if (s0.e_post) {
-                const float* ep = s0.e_post + (size_t)graph * ne;
+        for (int seg = c.seg + 1; seg < st.first_seg[c.q] + st.n_segs[c.q]; ++seg) {
+            int e0, e1b;
+            seg_range(seg, c.node, e0, e1b);
+            if (e1b > e0) return true;
+        }
+        return false;
+    };
+    auto advance = [&](const Chunk& c, int& e1) {   // returns the chunk after c; e1 = end of its segment
+        Chunk n = c;
+        n.first = false;
+        if (c.base + KC < e1) {
+            n.base = c.base + KC;
+            n.n = min(KC, e1 - n.base);
+            return n;
+        }
+#pragma unroll 1
+        for (int seg = c.seg + 1; seg < st.first_seg[c.q] + st.n_segs[c.q]; ++seg) {
+            int e0, e1b;
+            seg_range(seg, c.node, e0, e1b);
+            if (e1b > e0) {
+                n.seg = seg; n.base = e0; n.n = min(KC, e1b - e0);
+                e1 = e1b;
+                return n;
+            }
+        }
+        e1 = open_item(n, c.item + gridDim.x, c.q);
+        return n;
+    };
+    auto load_cols = [&](const Chunk& c, int b) {
+        const cb_tp_segment& sg = a.segs[c.seg];
+        if (tid < c.n) cols_of(b)[tid] = __ldg(sg.col + c.base + tid) + sg.col_off;
+    };
+    auto issue_gather = [&](const Chunk& c, int b) {   // cp.async: lands while the previous chunk is being multiplied
+        const cb_tp_segment& sg = a.segs[c.seg];
+        const int* cols = cols_of(b);
+        float* xs = xs_of(b);
+        float* Ps = ps_of(b);
+#pragma unroll 1
+        for (int e = warp; e < c.n; e += THREADS / 32) {
+            const float* xr = a.x + (size_t)cols[e] * d_in;
+#pragma unroll 1
+            for (int k = lane; k < d_in / 2; k += 32) cp_async_bytes8(xs + e * dxp + 2 * k, xr + 2 * k);
+            if (sg.P_nbr) {
+                const float* pr = sg.P_nbr + (size_t)cols[e] * sg.ldp_nbr;
+#pragma unroll 1
+                for (int k = lane; k < H / 4; k += 32) cp_async_bytes16(Ps + e * H + 4 * k, pr + 4 * k);
+            }
+        }
+#pragma unroll 1
+        for (int i = tid; i < c.n * S; i += THREADS) cp_async_bytes4(shs_of(b) + i, sg.sh + (size_t)c.base * S + i);
+#pragma unroll 1
+        for (int i = tid; i < c.n * (ne / 4); i += THREADS) cp_async_bytes16(es_of(b) + 4 * i, sg.e_attr + (size_t)c.base * ne + 4 * i);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+
+    Chunk cur;
+    int cur_e1 = open_item(cur, blockIdx.x, 0);
+    int buf = 0;
+    if (cur.valid) {
+        load_cols(cur, 0);
+        __syncthreads();
+        issue_gather(cur, 0);
+    }
+#pragma unroll 1
+    while (cur.valid) {
+        const cb_tp_segment& sg = a.segs[cur.seg];
+        const int n = cur.n;
+        cur.last = !has_more(cur, cur_e1);
+        int nxt_e1 = cur_e1;
+        Chunk nxt = advance(cur, nxt_e1);
+        if (nxt.valid) load_cols(nxt, buf ^ 1);
+        if (cur.first) {
+            // ---- per-item setup: edge-embedding slice of the first Linear (on slot change), constant part of h
+            const cb_tp_segment& s0 = a.segs[st.first_seg[cur.q]];
+            if (staged_slot != cur.q) {
+#pragma unroll 1
+                for (int i = tid; i < H * (ne / 4); i += THREADS) {
+                    const int qq = i / (ne / 4), c4 = i - qq * (ne / 4);
+                    *reinterpret_cast<float4*>(W1e_s + qq * nep + 4 * c4) =
+                        __ldg(reinterpret_cast<const float4*>(s0.W1e + (size_t)qq * s0.ldw1) + c4);
+                }
+                staged_slot = cur.q;
+                __syncthreads();
+            }
+            const int graph = a.agg_graph ? a.agg_graph[cur.node] : 0;
+#pragma unroll 1
+            for (int qq = tid; qq < H; qq += THREADS) {
+                float v = s0.b1[qq];
+                if (s0.P_agg) v += s0.P_agg[(size_t)cur.node * s0.ldp_agg + qq];
+                if (s0.e_post) {
+                    const float* ep = s0.e_post + (size_t)graph * ne;
 #pragma unroll 4
-                for (int c = 0; c < ne; ++c) v = fmaf(W1e_s[qq * nep + c], ep[c], v);
+                    for (int c = 0; c < ne; ++c) v = fmaf(W1e_s[qq * nep + c], ep[c], v);
+                }
+                hbase[qq] = v;
             }
-            hbase[qq] = v;
         }
-        bool first_mma = true;
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();                                   // gather(cur), cols(nxt), hbase visible to everyone
+        if (nxt.valid) issue_gather(nxt, buf ^ 1);         // overlaps everything below
 
-#pragma unroll 1
-        for (int s = seg0; s < seg0 + nseg; ++s) {
-            const cb_tp_segment& sg = a.segs[s];
-            const int e0 = sg.rowptr[node - sg.n0], e1 = sg.rowptr[node - sg.n0 + 1];
-#pragma unroll 1
-            for (int base = e0; base < e1; base += KC) {
-                const int n = min(KC, e1 - base);
-                // ---- gather raw operands (overlaps the MMAs of the previous chunk)
-                if (tid < n) cols_s[tid] = sg.col[base + tid] + sg.col_off;
-                __syncthreads();
-#pragma unroll 1
-                for (int e = warp; e < n; e += THREADS / 32) {
-                    const float* xr = a.x + (size_t)cols_s[e] * d_in;
-#pragma unroll 1
-                    for (int k = lane; k < d_in; k += 32) xs[e * dxp + k] = __ldg(xr + k);
-                    if (sg.P_nbr) {
-                        const float* pr = sg.P_nbr + (size_t)cols_s[e] * sg.ldp_nbr;
-#pragma unroll 1
-                        for (int k = lane; k < H; k += 32) Ps[e * H + k] = __ldg(pr + k);
-                    }
-                }
-#pragma unroll 1
-                for (int i = tid; i < n * S; i += THREADS) shs[i] = __ldg(sg.sh + (size_t)base * S + i);
-#pragma unroll 1
-                for (int i = tid; i < n * (ne / 4); i += THREADS)
-                    reinterpret_cast<float4*>(es)[i] = __ldg(reinterpret_cast<const float4*>(sg.e_attr + (size_t)base * ne) + i);
-                // the operand tiles are free once the previous chunk's MMAs have completed
-                if (waited < commits) {
-                    mbar_wait(&mma_bar, waited & 1);
-                    ++waited;
-                }
-                __syncthreads();
-                // ---- F^T tile: row r = f-row, column = edge; hi/lo TF32 split.  Loops stay rolled on purpose:
-                // the kernel must fit the 32 KB instruction cache (an unrolled build stalled on instruction fetch).
-                const int nq = 2 * ((n + 7) >> 3);   // 4-edge groups covered by the MMA k-steps of this chunk
-                if (tid < n_rows) {
-                    const int rbase = (tid >> 3) * SBO + (tid & 7) * 16;
-#pragma unroll 1
-                    for (int e4 = 0; e4 < nq; ++e4) {
-                        float v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int e = min(4 * e4 + j, n - 1);          // clamp: edges >= n are zeroed below
-                            const float* xe = xs + e * dxp;
-                            const float* se = shs + e * S;
-                            float acc = 0.0f;
-#pragma unroll
-                            for (int t = 0; t < MAXT; ++t) acc = fmaf(t_cf[t] * xe[t_xi[t]], se[t_si[t]], acc);
-                            v[j] = (4 * e4 + j < n) ? acc : 0.0f;
-                        }
-                        if (te0 - tb0 > MAXT) {   // rare long rows: finish from the shared-memory term table
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int e = 4 * e4 + j;
-                                if (e < n)
-#pragma unroll 1
-                                    for (int t = tb0 + MAXT; t < te0; ++t) {
-                                        const cb_tp_term tm = terms_s[t];
-                                        v[j] = fmaf(tm.coef * xs[e * dxp + tm.x_idx], shs[e * S + tm.sh_idx], v[j]);
-                                    }
-                            }
-                        }
-                        float4 hi, lo;
-                        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
-                        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
-                        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
-                        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
-                        lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
-                        *reinterpret_cast<float4*>(Fhi + rbase + e4 * LBO) = hi;   // 4 consecutive edges = one 16-byte core-matrix row
-                        *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
-                    }
-                }
-#pragma unroll 1
-                for (int r = tid + THREADS; r < n_rows; r += THREADS) {   // rows beyond the first 256 (lmax-2 layers)
-                    const int tb = rows_s[r].term_begin, te = rows_s[r].term_end;
-                    const int rbase = (r >> 3) * SBO + (r & 7) * 16;
-#pragma unroll 1
-                    for (int e4 = 0; e4 < nq; ++e4) {
-                        float v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int e = 4 * e4 + j;
-                            float acc = 0.0f;
-                            if (e < n)
-#pragma unroll 1
-                                for (int t = tb; t < te; ++t) {
-                                    const cb_tp_term tm = terms_s[t];
-                                    acc = fmaf(tm.coef * xs[e * dxp + tm.x_idx], shs[e * S + tm.sh_idx], acc);
-                                }
-                            v[j] = acc;
-                        }
-                        float4 hi, lo;
-                        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
-                        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
-                        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
-                        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
-                        lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
-                        *reinterpret_cast<float4*>(Fhi + rbase + e4 * LBO) = hi;
-                        *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
-                    }
-                }
-                // ---- H~ tile: row q = hidden unit (row H = constant 1), column = edge
-#pragma unroll 1
-                for (int i = tid; i < (H + 1) * 2; i += THREADS) {
-                    const int qq = i >> 1, half = i & 1;
-                    const float4* w4 = reinterpret_cast<const float4*>(W1e_s + qq * nep);
-                    const int rbase = (qq >> 3) * SBO + (qq & 7) * 16;
-#pragma unroll 1
-                    for (int e4 = half; e4 < nq; e4 += 2) {
-                        float v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int e = 4 * e4 + j;
-                            float acc = 0.0f;
-                            if (e < n) {
-                                if (qq == H) {
-                                    acc = 1.0f;
-                                } else {
-                                    acc = hbase[qq];
-                                    if (sg.P_nbr) acc += Ps[e * H + qq];
-                                    const float4* ev = reinterpret_cast<const float4*>(es + e * ne);
-#pragma unroll 2
-                                    for (int c = 0; c < ne / 4; ++c) {
-                                        const float4 w = w4[c], x4 = ev[c];
-                                        acc = fmaf(w.x, x4.x, acc);
-                                        acc = fmaf(w.y, x4.y, acc);
-                                        acc = fmaf(w.z, x4.z, acc);
-                                        acc = fmaf(w.w, x4.w, acc);
-                                    }
-                                    acc = fmaxf(acc, 0.0f);
-                                }
-                            }
-                            v[j] = acc;
-                        }
-                        float4 hi, lo;
-                        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
-                        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
-                        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
-                        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
-                        lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
-                        *reinterpret_cast<float4*>(Hhi + rbase + e4 * LBO) = hi;
-                        *reinterpret_cast<float4*>(Hlo + rbase + e4 * LBO) = lo;
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
-                __syncthreads();
-                // ---- one thread issues the MMAs of this chunk and commits them to the barrier
-                if (tid == 0) {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const int ksteps = (n + 7) >> 3;
-                    const uint32_t fhi = fhi_a, flo = flo_a, hhi = hhi_a, hlo = hlo_a;
-#pragma unroll 1
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t d = tmem_base + (uint32_t)(mt * NP);
-                        uint32_t acc = first_mma ? 0u : 1u;
-#pragma unroll 1
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t ao = (uint32_t)(mt * 16 * SBO + ks * 2 * LBO), bo = (uint32_t)(ks * 2 * LBO);
-                            mma_tf32(d, make_desc(fhi + ao), make_desc(hhi + bo), idesc, acc);
-                            mma_tf32(d, make_desc(fhi + ao), make_desc(hlo + bo), idesc, 1u);
-                            mma_tf32(d, make_desc(flo + ao), make_desc(hhi + bo), idesc, 1u);
-                            acc = 1u;
-                        }
-                    }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
-                                 : "memory");
-                }
-                first_mma = false;
-                ++commits;
-            }
-        }
-        // ---- epilogue: wait for the last MMAs, read the tile back from TMEM, write it to the workspace
-        while (waited < commits) {
+        if (waited < commits) {                            // operand tiles are free once the previous MMAs completed
             mbar_wait(&mma_bar, waited & 1);
             ++waited;
         }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* Aout = a.workspace + (size_t)item * n_rows * HA;
-        const int lg = warp & 3;                 // TMEM lane group this warp may access
+        const float* xs = xs_of(buf);
+        const float* shs = shs_of(buf);
+        const float* es = es_of(buf);
+        const float* Ps = ps_of(buf);
+        // ---- F^T tile: row r = f-row, column = edge; hi/lo TF32 split.  Loops stay rolled on purpose:
+        // the kernel must fit the 32 KB instruction cache (an unrolled build stalled on instruction fetch).
+        const int nq = 2 * ((n + 7) >> 3);   // 4-edge groups covered by the MMA k-steps of this chunk
+        if (tid < n_rows) {
+            const int rbase = (tid >> 3) * SBO + (tid & 7) * 16;
 #pragma unroll 1
-        for (int mt = warp >> 2; mt < MT; mt += THREADS / 128) {
-            const int r = mt * 128 + lg * 32 + lane;
-#pragma unroll 1
-            for (int c0 = 0; c0 < NP; c0 += 32) {   // NP is a multiple of 16; a trailing half chunk reads 16 spare columns
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * NP + c0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr));
-                if (c0 + 16 < NP)
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                        : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr + 16u));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (r < n_rows) {
-                    float* dst = Aout + (size_t)r * HA + c0;
+            for (int e4 = 0; e4 < nq; ++e4) {
+                float v[4];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (c0 + j < HA)
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                for (int j = 0; j < 4; ++j) {
+                    const int e = min(4 * e4 + j, n - 1);          // clamp: edges >= n are zeroed below
+                    const float* xe = xs + e * dxp;
+                    const float* se = shs + e * S;
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int t = 0; t < MAXT; ++t) acc = fmaf(t_cf[t] * xe[t_xi[t]], se[t_si[t]], acc);
+                    v[j] = (4 * e4 + j < n) ? acc : 0.0f;
                 }
+                if (te0 - tb0 > MAXT) {   // rare long rows: finish from the shared-memory term table
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int e = 4 * e4 + j;
+                        if (e < n)
+#pragma unroll 1
+                            for (int t = tb0 + MAXT; t < te0; ++t) {
+                                const cb_tp_term tm = terms_s[t];
+                                v[j] = fmaf(tm.coef * xs[e * dxp + tm.x_idx], shs[e * S + tm.sh_idx], v[j]);
+                            }
+                    }
+                }
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
+                hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
+                hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
+                hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
+                lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+                *reinterpret_cast<float4*>(Fhi + rbase + e4 * LBO) = hi;   // 4 consecutive edges = one 16-byte core-matrix row
+                *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int r = tid + THREADS; r < n_rows; r += THREADS) {   // rows beyond the first 256 (lmax-2 layers)
+            const int tb = rows_s[r].term_begin, te = rows_s[r].term_end;
+            const int rbase = (r >> 3) * SBO + (r & 7) * 16;
+#pragma unroll 1
+            for (int e4 = 0; e4 < nq; ++e4) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = 4 * e4 + j;
+                    float acc = 0.0f;
+                    if (e < n)
+#pragma unroll 1
+                        for (int t = tb; t < te; ++t) {
+                            const cb_tp_term tm = terms_s[t];
+                            acc = fmaf(tm.coef * xs[e * dxp + tm.x_idx], shs[e * S + tm.sh_idx], acc);
+                        }
+                    v[j] = acc;
+                }
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
+                hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
+                hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
+                hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
+                lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+                *reinterpret_cast<float4*>(Fhi + rbase + e4 * LBO) = hi;
+                *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
+            }
+        }
+        // ---- H~ tile: row q = hidden unit (row H = constant 1), column = edge
+#pragma unroll 1
+        for (int i = tid; i < (H + 1) * 2; i += THREADS) {
+            const int qq = i >> 1, half = i & 1;
+            const float4* w4 = reinterpret_cast<const float4*>(W1e_s + qq * nep);
+            const int rbase = (qq >> 3) * SBO + (qq & 7) * 16;
+#pragma unroll 1
+            for (int e4 = half; e4 < nq; e4 += 2) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = 4 * e4 + j;
+                    float acc = 0.0f;
+                    if (e < n) {
+                        if (qq == H) {
+                            acc = 1.0f;
+                        } else {
+                            acc = hbase[qq];
+                            if (sg.P_nbr) acc += Ps[e * H + qq];
+                            const float4* ev = reinterpret_cast<const float4*>(es + e * ne);
+#pragma unroll 2
+                            for (int c = 0; c < ne / 4; ++c) {
+                                const float4 w = w4[c], x4 = ev[c];
+                                acc = fmaf(w.x, x4.x, acc);
+                                acc = fmaf(w.y, x4.y, acc);
+                                acc = fmaf(w.z, x4.z, acc);
+                                acc = fmaf(w.w, x4.w, acc);
+                            }
+                            acc = fmaxf(acc, 0.0f);
+                        }
+                    }
+                    v[j] = acc;
+                }
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
+                hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
+                hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
+                hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
+                lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+                *reinterpret_cast<float4*>(Hhi + rbase + e4 * LBO) = hi;
+                *reinterpret_cast<float4*>(Hlo + rbase + e4 * LBO) = lo;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+        __syncthreads();
+        // ---- one thread issues the MMAs of this chunk and commits them to the barrier
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int ksteps = (n + 7) >> 3;
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t d = tmem_base + (uint32_t)(mt * NP);
+                uint32_t acc = cur.first ? 0u : 1u;
+#pragma unroll 1
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t ao = (uint32_t)(mt * 16 * SBO + ks * 2 * LBO), bo = (uint32_t)(ks * 2 * LBO);
+                    mma_tf32(d, make_desc(fhi_a + ao), make_desc(hhi_a + bo), idesc, acc);
+                    mma_tf32(d, make_desc(fhi_a + ao), make_desc(hlo_a + bo), idesc, 1u);
+                    mma_tf32(d, make_desc(flo_a + ao), make_desc(hhi_a + bo), idesc, 1u);
+                    acc = 1u;
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
+                         : "memory");
+        }
+        ++commits;
+        if (cur.last) {
+            // ---- epilogue: wait for the last MMAs, read the tile back from TMEM, write it to the workspace
+            while (waited < commits) {
+                mbar_wait(&mma_bar, waited & 1);
+                ++waited;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float* Aout = a.workspace + (size_t)cur.item * n_rows * HA;
+            const int lg = warp & 3;                 // TMEM lane group this warp may access
+#pragma unroll 1
+            for (int mt = warp >> 2; mt < MT; mt += THREADS / 128) {
+                const int r = mt * 128 + lg * 32 + lane;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NP; c0 += 32) {   // NP is a multiple of 16; a trailing half chunk reads 16 spare columns
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * NP + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                        : "r"(taddr));
+                    if (c0 + 16 < NP)
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                            : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                            : "r"(taddr + 16u));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (r < n_rows) {
+                        float* dst = Aout + (size_t)r * HA + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (c0 + j < HA)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();   // TMEM tile fully read before the next item's first MMA overwrites it
+        }
+        cur = nxt;
+        cur_e1 = nxt_e1;
+        buf ^= 1;
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
@@ -950,18 +1036,21 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
                      (long long)a->workspace_floats, (long long)items);
         int rc;
         if (a->accum_mode == 2) {
+            CB_CHECK_ARG(a->d_in % 2 == 0, "cb_tp_conv_forward: tcgen05 accumulate needs an even node-feature width (d_in=%d)", a->d_in);
             CB_CHECK_ARG(R <= 384 && ((R + 127) / 128) * ((H + 1 + 15) / 16 * 16) <= tc::TMEM_COLS,
                          "cb_tp_conv_forward: tcgen05 accumulate supports rows<=384 and tiles within 256 TMEM columns (rows=%d H=%d)", R, H);
             const tc::Layout L = tc::make_layout(R, a->n_terms, a->ne, a->d_in, a->S, H);
             // at least 80 KB so that never more than 2 CTAs (2 x 256 TMEM columns) share an SM
             const size_t smem = (size_t)(L.total > 80 * 1024 ? L.total : 80 * 1024);
-            CB_CHECK_ARG(smem <= 112 * 1024, "cb_tp_conv_forward: tcgen05 accumulate needs %zu B of shared memory", smem);
+            // <= 112 KB: two CTAs per SM; wider edge embeddings (generic layer call) run one CTA per SM
+            CB_CHECK_ARG(smem <= 220 * 1024, "cb_tp_conv_forward: tcgen05 accumulate needs %zu B of shared memory", smem);
             cudaError_t e = cudaFuncSetAttribute(tc::tp_accumulate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) {
                 cb_set_error("cb_tp_conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
                 return CB_ERR_CUDA;
             }
-            const int grid = items < CB_NUM_SMS * 2 ? (int)items : CB_NUM_SMS * 2;
+            const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+            const int grid = items < CB_NUM_SMS * per_sm ? (int)items : CB_NUM_SMS * per_sm;
             tc::tp_accumulate_tc_kernel<<<grid, tc::THREADS, smem, st>>>(*a, (int)items);
             CB_CHECK_LAUNCH("cb_tp_conv_forward(accumulate, tcgen05)");
             rc = CB_OK;

@@ -25,6 +25,7 @@ ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
 # accumulate kernel of K3: 2 = tcgen05 3xTF32 UMMA + TMEM accumulator (default);
 # 1 = fp32 FFMA register tiles (kept for shapes outside the UMMA tile limits and for A/B measurements)
 ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "2"))
+DEBUG_KEEP_WORKSPACE = None   # tests may set this to a list to inspect the K3 accumulators
 WORKSPACE_BYTES = 6 << 30  # cap on the K3 accumulator workspace; larger layers are processed in node chunks
 
 
@@ -223,7 +224,7 @@ class TensorProductConvLayer(nn.Module):
         per_item = P.n_rows * (H + 4)
         a.node_begin, a.node_end = 0, n_out
         np_cols = -(-(H + 1) // 16) * 16
-        tc_ok = P.n_rows <= 384 and -(-P.n_rows // 128) * np_cols <= 256
+        tc_ok = P.n_rows <= 384 and -(-P.n_rows // 128) * np_cols <= 256 and x.shape[1] % 2 == 0
         a.accum_mode = ACCUM_MODE if tc_ok else 1
         items = _lib.tp_conv_items(a)
         max_items = max(1, WORKSPACE_BYTES // (4 * per_item))
@@ -235,6 +236,8 @@ class TensorProductConvLayer(nn.Module):
             ws = torch.empty(max(it, 1) * per_item, dtype=torch.float32, device=dev)
             a.workspace, a.workspace_floats = ws.data_ptr(), ws.numel()
             _lib.tp_conv_forward(a)
+            if DEBUG_KEEP_WORKSPACE is not None:
+                DEBUG_KEEP_WORKSPACE.append(ws.view(-1, P.n_rows, H + 4))
         return out
 
     # ------------------------------------------------------------------ reference-style call
