@@ -38,7 +38,7 @@ class TpSegment(C.Structure):
         ("sh", C.c_void_p), ("P_agg", C.c_void_p), ("P_nbr", C.c_void_p),
         ("ldp_agg", C.c_int32), ("ldp_nbr", C.c_int32),
         ("W1e", C.c_void_p), ("ldw1", C.c_int32),
-        ("b1", C.c_void_p), ("W2", C.c_void_p), ("b2", C.c_void_p),
+        ("b1", C.c_void_p), ("W2a", C.c_void_p),
         ("n0", C.c_int32), ("n1", C.c_int32), ("col_off", C.c_int32), ("slot", C.c_int32),
     ]
 

@@ -8,7 +8,7 @@
 //             (R rows; FasterTensorProduct's out_dict entries tensor_layers.py:72-85, or one row
 //             per (e3nn instruction, u, k))
 //   h~_e    : [relu(W1 a_e + b1) ; 1]  (H+1 columns), the hidden layer of the radial MLP (layers.py:8-15)
-//   T_q(A)[o(r,m)] += sum_j W2[w(r)+m][j] A[r][j] + b2[w(r)+m] A[r][H]
+//   T_q(A)[o(r,m)] += sum_j W2[w(r)+m][j] A[r][j] + b2[w(r)+m] A[r][H]     (W2a = [W2 | b2 | 0 0 0] row-wise)
 // so the [E, weight_numel] per-edge weight tensor of the reference (6.6 KB per edge) is never formed.
 //
 // Two kernels:
@@ -27,17 +27,26 @@ namespace {
 
 constexpr int CH = 32;   // edges staged per chunk in the accumulate kernel
 constexpr int PADC = 4;  // extra workspace columns per row: [H] = sum_e f_e, [H+1..H+3] = 0
+// Workspace layout.  The aggregation nodes are cut into tiles of WS_TILE consecutive nodes (counted from
+// node_begin; one transform CTA per tile).  For every (slot, tile) the accumulators of the tile's active nodes
+// (>= 1 edge in the slot) are stored row-major over (row r, rank of the node among the tile's active nodes):
+//     A[(tile_off[q] + tile) * R * WS_TILE * HA  +  (r * n_act + rank) * HA  +  j]
+// so the transform kernel fetches a whole row group of a tile with ONE contiguous bulk copy.
+constexpr int WS_TILE = 32;
 
 struct SlotTable {
     int n_slots;
     int first_seg[CB_MAX_SEGS], n_segs[CB_MAX_SEGS];
     int lo[CB_MAX_SEGS], hi[CB_MAX_SEGS];   // node range of the slot clipped to [node_begin, node_end)
     int item_off[CB_MAX_SEGS + 1];
+    int tile0[CB_MAX_SEGS];                 // first node tile of the slot (tiles of WS_TILE nodes counted from node_begin)
+    int tile_off[CB_MAX_SEGS + 1];          // workspace tiles before the slot
 };
 
 __host__ __device__ inline void build_slots(const cb_tp_conv_args& a, SlotTable& t) {
     t.n_slots = 0;
     t.item_off[0] = 0;
+    t.tile_off[0] = 0;
     for (int s = 0; s < a.n_segs; ++s) {
         if (s > 0 && a.segs[s].slot == a.segs[s - 1].slot) {
             t.n_segs[t.n_slots - 1]++;
@@ -51,7 +60,29 @@ __host__ __device__ inline void build_slots(const cb_tp_conv_args& a, SlotTable&
         t.lo[q] = lo;
         t.hi[q] = hi > lo ? hi : lo;
         t.item_off[q + 1] = t.item_off[q] + (t.hi[q] - t.lo[q]);
+        t.tile0[q] = (t.lo[q] - a.node_begin) / WS_TILE;
+        t.tile_off[q + 1] = t.tile_off[q] + (t.hi[q] > t.lo[q] ? (t.hi[q] - a.node_begin + WS_TILE - 1) / WS_TILE - t.tile0[q] : 0);
     }
+}
+
+// Where the accumulator of (slot q, node) lives: called by all 32 lanes of a warp (lane = node of the tile).
+// Returns the float offset of element (row 0, column 0) and the row stride in floats.
+__device__ __forceinline__ size_t ws_place(const cb_tp_conv_args& a, const SlotTable& st, int q, int node, int n_rows, int HA, int lane,
+                                           int& row_stride) {
+    const int tile = (node - a.node_begin) / WS_TILE;
+    const int other = a.node_begin + tile * WS_TILE + lane;
+    int deg = 0;
+    if (other >= st.lo[q] && other < st.hi[q]) {
+#pragma unroll 1
+        for (int s = st.first_seg[q]; s < st.first_seg[q] + st.n_segs[q]; ++s) {
+            const cb_tp_segment& sg = a.segs[s];
+            deg += __ldg(sg.rowptr + (other - sg.n0) + 1) - __ldg(sg.rowptr + (other - sg.n0));
+        }
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, deg > 0);
+    const int rank = __popc(act & ((1u << (node - a.node_begin - tile * WS_TILE)) - 1u));
+    row_stride = __popc(act) * HA;
+    return ((size_t)(st.tile_off[q] + tile - st.tile0[q]) * n_rows * WS_TILE + rank) * HA;
 }
 
 // ------------------------------------------------------------------------------------------ (a)
@@ -273,18 +304,19 @@ tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
         }
 
         // ---- write the finished tile: A[item][r][0..H) and column H = sum_e f_e[r]
-        float* Aout = a.workspace + (size_t)item * n_rows * HA;
+        int row_stride;
+        float* Aout = a.workspace + ws_place(a, st, q, node, n_rows, HA, threadIdx.x & 31, row_stride);
 #pragma unroll
         for (int i = 0; i < TR; ++i) {
             const int r = tr * TR + i;
             if (r < n_rows) {
-                float* dst = Aout + (size_t)r * HA + tc * TC;
+                float* dst = Aout + (size_t)r * row_stride + tc * TC;
 #pragma unroll
                 for (int j4 = 0; j4 < TC / 4; ++j4)
                     if (tc * TC + 4 * j4 < H)
                         *reinterpret_cast<float4*>(dst + 4 * j4) =
                             make_float4(acc[i][4 * j4], acc[i][4 * j4 + 1], acc[i][4 * j4 + 2], acc[i][4 * j4 + 3]);
-                if (tc == 0) *reinterpret_cast<float4*>(Aout + (size_t)r * HA + H) = make_float4(fsum[i], 0.f, 0.f, 0.f);
+                if (tc == 0) *reinterpret_cast<float4*>(Aout + (size_t)r * row_stride + H) = make_float4(fsum[i], 0.f, 0.f, 0.f);
             }
         }
     }
@@ -314,6 +346,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
 }
 
+// 3xTF32 operand split: hi = x rounded to the 10-bit TF32 mantissa, lo = (x - hi) rounded likewise (the tensor
+// core ignores the low 13 bits, so rounding here keeps the error unbiased)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
+
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -335,9 +374,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
     __trap();  // never hang the GPU: a lost MMA completion aborts the kernel instead
 }
-
-// byte offset of element (row, k) inside an operand tile
-__device__ __forceinline__ int tile_off(int row, int k) { return (row >> 3) * SBO + (k >> 2) * LBO + (row & 7) * 16 + (k & 3) * 4; }
 
 struct Layout {
     int rows, terms, w1e, hbase, cols, xs, shs, es, ps, fhi, flo, hhi, hlo, total;  // byte offsets
@@ -629,11 +665,10 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     }
                 }
                 float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
-                hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
-                hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
-                hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
-                lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+                split_tf32(v[0], hi.x, lo.x);
+                split_tf32(v[1], hi.y, lo.y);
+                split_tf32(v[2], hi.z, lo.z);
+                split_tf32(v[3], hi.w, lo.w);
                 *reinterpret_cast<float4*>(Fhi + rbase + e4 * LBO) = hi;   // 4 consecutive edges = one 16-byte core-matrix row
                 *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
             }
@@ -658,11 +693,10 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     v[j] = acc;
                 }
                 float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
-                hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
-                hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
-                hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
-                lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+                split_tf32(v[0], hi.x, lo.x);
+                split_tf32(v[1], hi.y, lo.y);
+                split_tf32(v[2], hi.z, lo.z);
+                split_tf32(v[3], hi.w, lo.w);
                 *reinterpret_cast<float4*>(Fhi + rbase + e4 * LBO) = hi;
                 *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
             }
@@ -701,11 +735,10 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     v[j] = acc;
                 }
                 float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u);
-                hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u);
-                hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u);
-                hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u);
-                lo = make_float4(v[0] - hi.x, v[1] - hi.y, v[2] - hi.z, v[3] - hi.w);
+                split_tf32(v[0], hi.x, lo.x);
+                split_tf32(v[1], hi.y, lo.y);
+                split_tf32(v[2], hi.z, lo.z);
+                split_tf32(v[3], hi.w, lo.w);
                 *reinterpret_cast<float4*>(Hhi + rbase + e4 * LBO) = hi;
                 *reinterpret_cast<float4*>(Hlo + rbase + e4 * LBO) = lo;
             }
@@ -740,7 +773,8 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 ++waited;
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float* Aout = a.workspace + (size_t)cur.item * n_rows * HA;
+            int row_stride;
+            float* Aout = a.workspace + ws_place(a, st, cur.q, cur.node, n_rows, HA, lane, row_stride);
             const int lg = warp & 3;                 // TMEM lane group this warp may access
 #pragma unroll 1
             for (int mt = warp >> 2; mt < MT; mt += THREADS / 128) {
@@ -762,7 +796,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                             : "r"(taddr + 16u));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (r < n_rows) {
-                        float* dst = Aout + (size_t)r * HA + c0;
+                        float* dst = Aout + (size_t)r * row_stride + c0;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             if (c0 + j < HA)
@@ -788,183 +822,276 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------ (b)
-constexpr int NB = 32;        // nodes per CTA
-constexpr int TT = 256;       // threads
-constexpr int MAX_RS = 2;     // rows of a run processed concurrently
-constexpr int MAX_WROWS = 32; // weight rows staged per row group (RS * mul): mul <= 32
-constexpr int MAX_PASS = 2;
+// Transform kernel.  One CTA per 32 aggregation nodes.  For every slot with edges into the tile and every run
+// (rows with the same output block and multiplicity `mul`) it computes
+//     out[n][out_base + m*out_step] += sum_r sum_j A[n][r][j] * W2a[w(r)+m][j]      (column H of W2a = b2)
+// Warp specialised: one producer warp streams the A rows (one 1-D bulk copy per node and row) and the
+// contiguous W2a rows of a row group into a 4-stage shared-memory ring with cp.async.bulk + mbarrier
+// complete_tx; 14 consumer warps wait on the stage's "full" barrier, compute, and release it through its
+// "empty" barrier -- no CTA-wide barrier per row group.
+// Register tiling of the consumers: a thread owns 4 nodes x MT outputs x one 4-column chunk of K (8 node lanes
+// x 28 K-chunks x 2 combos; a combo is the second row of a 2-row group for mul <= 8, or the upper half of the
+// outputs for mul > 8) and keeps its partial sums in registers over all rows of the run: per row 4 LDS.128
+// of A (node lanes interleaved => conflict-free), MT broadcast LDS.128 of W2a and 16*MT FMAs.  At the end of a
+// run the partials are reduced in a fixed order (shuffles over the 4 K-chunks of a warp, then shared memory
+// over warps).  Epilogue: mean over all incoming edges, BatchNorm(eval) affine, residual.
+namespace tf {
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+constexpr int NB = WS_TILE;     // nodes per CTA = one workspace tile
+static_assert(NB == 32, "the producer warp and the rank ballots map one lane to one node of the tile");
+constexpr int NT = 4;           // nodes per thread: node lane nl owns nodes nl, nl+8, nl+16, nl+24
+constexpr int WPC = 7;          // warps per combo (each warp: 8 node lanes x 4 K-chunks)
+constexpr int KSTRIDE = 4 * WPC;
+constexpr int CWARPS = 2 * WPC; // consumer warps
+constexpr int CT = 32 * CWARPS; // 448 consumer threads
+constexpr int TT = CT + 32;     // + the producer warp
+constexpr int STAGES = 4;
+constexpr int MAX_RS = 2;
+constexpr int MAX_WROWS = 32;
+constexpr int MTMAX = 16;
+constexpr int MAX_RUNS = 96;
+
+using tc::mbar_wait;
+using tc::smem_u32;
+
+struct Layout {
+    int a_stage, w_stage, stage, zero, part, outacc, items, total;   // floats
+};
+__host__ __device__ inline Layout make_layout(int H, int d_out, int n_slots) {
+    Layout L;
+    const int HA = H + PADC;
+    L.a_stage = MAX_RS * NB * HA;
+    L.w_stage = MAX_WROWS * HA;
+    L.stage = L.a_stage + L.w_stage;
+    int o = STAGES * L.stage;
+    L.zero = o;   o += HA;
+    L.part = o;   o += CWARPS * 8 * NT * MTMAX;
+    L.outacc = o; o += (NB * d_out + 3) & ~3;
+    L.items = o;  o += n_slots * NB;
+    L.total = o;
+    return L;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__global__ void __launch_bounds__(TT, 2)
+struct RunS { int row_begin, row_end, mul, w_base0, out_base, out_step, mt, rs; };
+
+__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// one row of one combo: acc[j][m] += A[node nl+8j][4kc..4kc+3] . W[m][4kc..4kc+3]
+template <int MT>
+__device__ __forceinline__ void row_fma(const float* const (&ap)[NT], const float* __restrict__ Wb, int HA, int a4, int kc, int nvalid,
+                                        float (&acc)[NT][MTMAX]) {
+#pragma unroll 1
+    for (int k = kc; k < a4; k += KSTRIDE) {
+        float4 av[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) av[j] = *reinterpret_cast<const float4*>(ap[j] + 4 * k);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            // outputs beyond the run's multiplicity read row 0 and are discarded by the reduction
+            const float4 w = *reinterpret_cast<const float4*>(Wb + (m < nvalid ? m : 0) * HA + 4 * k);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                acc[j][m] = fmaf(av[j].x, w.x, acc[j][m]);
+                acc[j][m] = fmaf(av[j].y, w.y, acc[j][m]);
+                acc[j][m] = fmaf(av[j].z, w.z, acc[j][m]);
+                acc[j][m] = fmaf(av[j].w, w.w, acc[j][m]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TT, 1)
 tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     const int H = a.H, HA = H + PADC, d_out = a.d_out, n_rows = a.n_rows;
-    const int a4 = HA / 4, h4 = H / 4;
-    const int A_STAGE = MAX_RS * NB * HA, W_STAGE = MAX_WROWS * HA;
-    float* As = sm;                                 // [2][MAX_RS][NB][HA]   (stage 0 aliased by the rs-reduction buffer)
-    float* Ws = As + 2 * A_STAGE;                   // [2][MAX_WROWS][HA]
-    float* outacc = Ws + 2 * W_STAGE;               // [NB][d_out]
+    const int a4 = HA / 4;
     __shared__ SlotTable st;
-    __shared__ int item_s[NB], deg_tot[NB];
-    __shared__ int any_valid;
+    __shared__ int active[CB_MAX_SEGS], n_items_s[CB_MAX_SEGS], deg_tot[NB];
+    __shared__ RunS run_s[MAX_RUNS];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = a.node_begin + blockIdx.x * NB;
-    if (tid == 0) build_slots(a, st);
-    for (int i = tid; i < NB * d_out; i += TT) outacc[i] = 0.0f;
-    if (tid < NB) deg_tot[tid] = 0;
+    if (tid == 0) {
+        build_slots(a, st);
+        for (int s = 0; s < STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full_bar[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&empty_bar[s])), "r"(CWARPS));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    const Layout L = make_layout(H, d_out, st.n_slots);
+    float* part = sm + L.part;        // [CWARPS][8 node lanes][NT][MTMAX]
+    float* outacc = sm + L.outacc;    // [NB][d_out]
+    int* items = reinterpret_cast<int*>(sm + L.items);   // [active slot][NB] rank of the node among the tile's active nodes, or -1
 
+    // ---- per-CTA tables
+#pragma unroll 1
+    for (int ri = tid; ri < a.n_runs; ri += TT) {
+        const cb_tp_run rn = a.runs[ri];
+        RunS s;
+        s.row_begin = rn.row_begin; s.row_end = rn.row_end; s.mul = rn.mul; s.w_base0 = rn.w_base0;
+        s.out_base = rn.out_base; s.out_step = rn.out_step;
+        // mul <= 8: all outputs in one thread tile, two rows per group; else the outputs are split over the two combos
+        s.mt = rn.mul <= 8 ? ((rn.mul + 1) & ~1) : (rn.mul <= 16 ? 8 : (rn.mul <= 24 ? 12 : 16));
+        s.rs = rn.mul <= 8 ? 2 : 1;
+        run_s[ri] = s;
+    }
+#pragma unroll 1
+    for (int i = tid; i < NB * d_out; i += TT) outacc[i] = 0.0f;
+    if (tid < HA) sm[L.zero + tid] = 0.0f;
+    if (tid < NB) deg_tot[tid] = 0;
+    int n_active = 0;
+#pragma unroll 1
     for (int q = 0; q < st.n_slots; ++q) {
-        if (t0 + NB <= st.lo[q] || t0 >= st.hi[q]) continue;   // block-uniform
-        if (tid == 0) any_valid = 0;
-        __syncthreads();
+        int it = -1;
         if (tid < NB) {
             const int node = t0 + tid;
             int deg = 0;
             if (node >= st.lo[q] && node < st.hi[q]) {
+#pragma unroll 1
                 for (int s = st.first_seg[q]; s < st.first_seg[q] + st.n_segs[q]; ++s) {
                     const cb_tp_segment& sg = a.segs[s];
                     deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
                 }
             }
-            item_s[tid] = deg > 0 ? st.item_off[q] + (node - st.lo[q]) : -1;
+            if (deg > 0) it = 0;
             deg_tot[tid] += deg;
-            if (deg > 0) any_valid = 1;
         }
-        __syncthreads();
-        const int slot_has_edges = any_valid;
-        __syncthreads();  // everyone has read the flag before the next slot resets it
-        if (!slot_has_edges) continue;
-        const cb_tp_segment& s0 = a.segs[st.first_seg[q]];
+        if (tid < 32) {                            // NB == 32: warp 0 ranks the active nodes
+            const unsigned act = __ballot_sync(0xffffffffu, it >= 0);
+            items[n_active * NB + tid] = it >= 0 ? __popc(act & ((1u << tid) - 1u)) : -1;
+        }
+        const int cnt = __syncthreads_count(it >= 0);
+        if (cnt > 0) {                             // slots without any edge into this tile are skipped
+            if (tid == 0) { active[n_active] = q; n_items_s[n_active] = cnt; }
+            ++n_active;
+        }
+    }
+    if (a.n_runs == 0) n_active = 0;
+    __syncthreads();
 
-        for (int ri = 0; ri < a.n_runs; ++ri) {
-            const cb_tp_run run = a.runs[ri];
-            const int mul = run.mul;
-            // work item = (row slot, node, output chunk); MT strided outputs per item, chosen to fill the CTA
-            const int MT = mul >= 16 ? 4 : (mul >= 4 ? 2 : 1);
-            const int MC = (mul + MT - 1) / MT;
-            int RS = TT / (NB * MC);
-            RS = RS < 1 ? 1 : (RS > MAX_RS ? MAX_RS : RS);
-            if (RS * mul > MAX_WROWS) RS = 1;
-            const int n_items = RS * NB * MC;
-            const int n_groups = (run.row_end - run.row_begin + RS - 1) / RS;
-            float acc[MAX_PASS][4];
-#pragma unroll
-            for (int p = 0; p < MAX_PASS; ++p)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[p][k] = 0.0f;
+    // ---- group sequence: (active slot k, run ri, row group starting at row rg)
+    struct Iter { int k, ri, rg; };
+    auto advance = [&](Iter& it) {
+        it.rg += run_s[it.ri].rs;
+        if (it.rg >= run_s[it.ri].row_end) {
+            if (++it.ri == a.n_runs) { it.ri = 0; ++it.k; }
+            it.rg = run_s[it.ri].row_begin;
+        }
+    };
+    Iter cur{0, 0, a.n_runs > 0 ? run_s[0].row_begin : 0};
 
-            // asynchronous staging of one row group: A rows [nrs][NB][HA] (zeros for nodes without edges in this
-            // slot) and the weight rows W2[w_base0 + (rg - row_begin + rs)*mul + m][0..H), column H = b2
-            auto prefetch = [&](int g, int buf) {
-                const int rg = run.row_begin + g * RS;
-                const int nrs = min(RS, run.row_end - rg);
-                float* Ab = As + buf * A_STAGE;
-                float* Wb = Ws + buf * W_STAGE;
-                // 8 threads per staged row: no integer division in the copy loops
-                const int sub = tid & 7;
-                for (int rn = tid >> 3; rn < nrs * NB; rn += TT / 8) {
-                    const int n = rn & (NB - 1), rs = rn / NB;
-                    float* dst = Ab + rn * HA;
-                    const int it = item_s[n];
-                    if (it >= 0) {
-                        const float* src = a.workspace + ((size_t)it * n_rows + rg + rs) * HA;
-                        for (int c4 = sub; c4 < a4; c4 += 8) cp_async16(dst + 4 * c4, src + 4 * c4);
-                    } else {
-                        for (int c4 = sub; c4 < a4; c4 += 8) *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                const int wrow0 = run.w_base0 + (rg - run.row_begin) * mul;
-                for (int wr = tid >> 3; wr < nrs * mul; wr += TT / 8) {
-                    const float* src = s0.W2 + (size_t)(wrow0 + wr) * H;
-                    float* dst = Wb + wr * HA;
-                    for (int c4 = sub; c4 < h4; c4 += 8) cp_async16(dst + 4 * c4, src + 4 * c4);
-                }
-                for (int wr = tid; wr < nrs * mul; wr += TT)
-                    *reinterpret_cast<float4*>(Wb + wr * HA + H) = make_float4(__ldg(s0.b2 + wrow0 + wr), 0.f, 0.f, 0.f);
-                cp_async_commit();
-            };
-
-            __syncthreads();  // buffers free (previous run's reduction done)
-            prefetch(0, 0);
-            for (int g = 0; g < n_groups; ++g) {
-                const int buf = g & 1;
-                if (g + 1 < n_groups) {
-                    prefetch(g + 1, buf ^ 1);
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                __syncthreads();
-                const int nrs = min(RS, run.row_end - (run.row_begin + g * RS));
-                const float* Ab = As + buf * A_STAGE;
-                const float* Wb = Ws + buf * W_STAGE;
+    if (warp == CWARPS) {
+        // ================= producer warp: lane = node of the tile
+#pragma unroll 1
+        for (int G = 0; cur.k < n_active; ++G) {
+            const int s = G % STAGES;
+            mbar_wait(&empty_bar[s], ((G / STAGES) & 1) ^ 1);
+            const RunS& run = run_s[cur.ri];
+            const cb_tp_segment& s0 = a.segs[st.first_seg[active[cur.k]]];
+            const int nrs = min(run.rs, run.row_end - cur.rg);
+            float* Ab = sm + s * L.stage;
+            float* Wb = Ab + L.a_stage;
+            const uint32_t row_bytes = (uint32_t)HA * 4u;
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)nrs * (uint32_t)(n_items_s[cur.k] + run.mul) * row_bytes;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full_bar[s])), "r"(bytes) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // the tile's active rows of the group are contiguous in the workspace: [row][rank][HA]
+                const int q = active[cur.k], n_act = n_items_s[cur.k];
+                const float* src = a.workspace + ((size_t)(st.tile_off[q] + (int)blockIdx.x - st.tile0[q]) * n_rows * WS_TILE + (size_t)cur.rg * n_act) * HA;
+                bulk_g2s(Ab, src, (uint32_t)(nrs * n_act) * row_bytes, &full_bar[s]);
+                const int wrow0 = run.w_base0 + (cur.rg - run.row_begin) * run.mul;
+                bulk_g2s(Wb, s0.W2a + (size_t)wrow0 * HA, (uint32_t)(nrs * run.mul) * row_bytes, &full_bar[s]);
+            }
+            advance(cur);
+        }
+    } else {
+        // ================= consumer warps
+        const int nl = lane & 7, combo = warp / WPC, kc = (warp % WPC) * 4 + (lane >> 3);
+        const float* zrow = sm + L.zero;
+        float acc[NT][MTMAX];
 #pragma unroll
-                for (int p = 0; p < MAX_PASS; ++p) {
-                    const int itx = tid + p * TT;
-                    if (itx < n_items) {
-                        const int mc = itx % MC, n = (itx / MC) % NB, rs = itx / (MC * NB);
-                        if (rs < nrs) {
-                            const float4* ap = reinterpret_cast<const float4*>(Ab + (rs * NB + n) * HA);
-                            // rows of the strided outputs m = mc + k*MC; outputs beyond mul read row 0 and are discarded
-                            const float4* wp[4];
+        for (int j = 0; j < NT; ++j)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const int m = mc + k * MC;
-                                wp[k] = reinterpret_cast<const float4*>(Wb + (rs * mul + ((k < MT && m < mul) ? m : 0)) * HA);
-                            }
-#pragma unroll 5
-                            for (int c4 = 0; c4 < a4; ++c4) {
-                                const float4 av = ap[c4];
+            for (int m = 0; m < MTMAX; ++m) acc[j][m] = 0.0f;
+        int rank[NT] = {-1, -1, -1, -1};
+        int has_k = -1, n_act = 0;
+#pragma unroll 1
+        for (int G = 0; cur.k < n_active; ++G) {
+            const int s = G % STAGES;
+            if (cur.k != has_k) {
+                has_k = cur.k;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (k < MT) {
-                                        const float4 w = wp[k][c4];
-                                        acc[p][k] = fmaf(av.x, w.x, acc[p][k]);
-                                        acc[p][k] = fmaf(av.y, w.y, acc[p][k]);
-                                        acc[p][k] = fmaf(av.z, w.z, acc[p][k]);
-                                        acc[p][k] = fmaf(av.w, w.w, acc[p][k]);
-                                    }
-                                }
-                            }
+                for (int j = 0; j < NT; ++j) rank[j] = items[cur.k * NB + nl + 8 * j];
+                n_act = n_items_s[cur.k];
+            }
+            const RunS run = run_s[cur.ri];
+            const int nrs = min(run.rs, run.row_end - cur.rg);
+            const float* Ab = sm + s * L.stage;
+            const float* Wb = Ab + L.a_stage;
+            // combo -> (row of the group, first output of the thread tile)
+            const int rs = run.rs == 2 ? combo : 0;
+            const int m0 = run.rs == 2 ? 0 : combo * run.mt;
+            mbar_wait(&full_bar[s], (G / STAGES) & 1);
+            if (rs < nrs && m0 < run.mul) {
+                const float* ap[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) ap[j] = rank[j] >= 0 ? Ab + (rs * n_act + rank[j]) * HA : zrow;   // nodes without edges read zeros
+                const float* wp = Wb + (rs * run.mul + m0) * HA;
+                const int nvalid = run.mul - m0;
+                switch (run.mt) {
+                    case 2: row_fma<2>(ap, wp, HA, a4, kc, nvalid, acc); break;
+                    case 4: row_fma<4>(ap, wp, HA, a4, kc, nvalid, acc); break;
+                    case 6: row_fma<6>(ap, wp, HA, a4, kc, nvalid, acc); break;
+                    case 8: row_fma<8>(ap, wp, HA, a4, kc, nvalid, acc); break;
+                    case 12: row_fma<12>(ap, wp, HA, a4, kc, nvalid, acc); break;
+                    default: row_fma<16>(ap, wp, HA, a4, kc, nvalid, acc); break;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+            if (cur.rg + run.rs >= run.row_end) {
+                // ---- end of the run: reduce the partial sums in a fixed order and add into the output channels
+                asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");   // the previous run's reducers are done with `part`
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int m = 0; m < MTMAX; ++m) {
+                        if (m < run.mt) {       // uniform
+                            float v = acc[j][m];
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            v += __shfl_xor_sync(0xffffffffu, v, 16);
+                            if (lane < 8) part[((warp * 8 + nl) * NT + j) * MTMAX + m] = v;
                         }
+                        acc[j][m] = 0.0f;
                     }
-                }
-                __syncthreads();  // stage `buf` may be refilled by the prefetch of group g+2
-            }
-            // ---- reduce over the row slots in fixed order and add into the output channels
-            float* part = As;  // [RS][NB][mul]  (all stages are idle here)
-#pragma unroll
-            for (int p = 0; p < MAX_PASS; ++p) {
-                const int itx = tid + p * TT;
-                if (itx < n_items) {
-                    const int mc = itx % MC, n = (itx / MC) % NB, rs = itx / (MC * NB);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int m = mc + k * MC;
-                        if (k < MT && m < mul) part[(rs * NB + n) * mul + m] = acc[p][k];
-                    }
+                asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
+#pragma unroll 1
+                for (int i = tid; i < NB * run.mul; i += CT) {
+                    const int m = i % run.mul, n = i / run.mul;
+                    const int c_lo = run.rs == 2 ? 0 : m / run.mt, c_hi = run.rs == 2 ? 2 : c_lo + 1;
+                    const int mm = run.rs == 2 ? m : m - c_lo * run.mt;
+                    float v = 0.0f;
+#pragma unroll 1
+                    for (int w = c_lo * WPC; w < c_hi * WPC; ++w) v += part[((w * 8 + (n & 7)) * NT + (n >> 3)) * MTMAX + mm];
+                    outacc[n * d_out + run.out_base + m * run.out_step] += v;
                 }
             }
-            __syncthreads();
-            for (int i = tid; i < NB * mul; i += TT) {
-                const int m = i % mul, n = i / mul;
-                float v = 0.0f;
-                for (int rs = 0; rs < RS; ++rs) v += part[(rs * NB + n) * mul + m];
-                outacc[n * d_out + run.out_base + m * run.out_step] += v;
-            }
+            advance(cur);
         }
     }
     __syncthreads();
     // ---- epilogue: mean over all incoming edges, BatchNorm (eval) affine, residual
+#pragma unroll 1
     for (int i = tid; i < NB * d_out; i += TT) {
         const int n = i / d_out, o = i - n * d_out;
         const int node = t0 + n;
@@ -976,6 +1103,8 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
         }
     }
 }
+
+}  // namespace tf
 
 template <class C>
 int launch_accumulate(const cb_tp_conv_args* a, int items, cudaStream_t st) {
@@ -999,7 +1128,7 @@ extern "C" int64_t cb_tp_conv_items(const cb_tp_conv_args* a) {
     if (a == nullptr || a->n_segs < 0 || a->n_segs > CB_MAX_SEGS) return -1;
     SlotTable t;
     build_slots(*a, t);
-    return t.item_off[t.n_slots];
+    return (int64_t)t.tile_off[t.n_slots] * WS_TILE;
 }
 
 extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
@@ -1015,25 +1144,28 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
                  a->node_begin, a->node_end, a->n_out);
     for (int s = 0; s < a->n_segs; ++s) {
         const cb_tp_segment& g = a->segs[s];
-        CB_CHECK_ARG(g.rowptr && g.col && g.e_attr && g.sh && g.W1e && g.b1 && g.W2 && g.b2, "cb_tp_conv_forward: segment %d has a null pointer", s);
+        CB_CHECK_ARG(g.rowptr && g.col && g.e_attr && g.sh && g.W1e && g.b1 && g.W2a, "cb_tp_conv_forward: segment %d has a null pointer", s);
         CB_CHECK_ARG(0 <= g.n0 && g.n0 <= g.n1 && g.n1 <= a->n_out, "cb_tp_conv_forward: segment %d node range [%d,%d) outside [0,%d)", s, g.n0, g.n1, a->n_out);
         if (s > 0) {
             const cb_tp_segment& p = a->segs[s - 1];
             CB_CHECK_ARG(g.slot == p.slot || g.slot == p.slot + 1, "cb_tp_conv_forward: slots must be consecutive in segment order");
             if (g.slot == p.slot)
-                CB_CHECK_ARG(g.n0 == p.n0 && g.n1 == p.n1 && g.W2 == p.W2 && g.W1e == p.W1e && g.P_agg == p.P_agg && g.e_post == p.e_post,
+                CB_CHECK_ARG(g.n0 == p.n0 && g.n1 == p.n1 && g.W2a == p.W2a && g.W1e == p.W1e && g.P_agg == p.P_agg && g.e_post == p.e_post,
                              "cb_tp_conv_forward: segments of slot %d must share node range and radial MLP", g.slot);
         } else {
             CB_CHECK_ARG(g.slot == 0, "cb_tp_conv_forward: first segment must be slot 0");
         }
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t items = cb_tp_conv_items(a);
+    SlotTable t;
+    build_slots(*a, t);
+    const int64_t ws_items = (int64_t)t.tile_off[t.n_slots] * WS_TILE;   // accumulator slots of the workspace (cb_tp_conv_items)
+    const int64_t items = t.item_off[t.n_slots];                          // (node, slot) pairs the accumulate kernel visits
     const int H = a->H, R = a->n_rows;
     if (items > 0) {
-        CB_CHECK_ARG(a->workspace != nullptr && a->workspace_floats >= items * (int64_t)R * (H + PADC),
+        CB_CHECK_ARG(a->workspace != nullptr && a->workspace_floats >= ws_items * (int64_t)R * (H + PADC),
                      "cb_tp_conv_forward: workspace too small (%lld floats for %lld accumulators)",
-                     (long long)a->workspace_floats, (long long)items);
+                     (long long)a->workspace_floats, (long long)ws_items);
         int rc;
         if (a->accum_mode == 2) {
             CB_CHECK_ARG(a->d_in % 2 == 0, "cb_tp_conv_forward: tcgen05 accumulate needs an even node-feature width (d_in=%d)", a->d_in);
@@ -1066,16 +1198,17 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
         if (rc != CB_OK) return rc;
     }
     // transform + epilogue
-    const int HA = H + PADC;
-    const size_t smem = sizeof(float) * (2 * (size_t)MAX_RS * NB * HA + 2 * (size_t)MAX_WROWS * HA + (size_t)NB * a->d_out);
-    CB_CHECK_ARG(smem <= 110 * 1024, "cb_tp_conv_forward: transform kernel needs %zu B of shared memory", smem);
-    cudaError_t e = cudaFuncSetAttribute(tp_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CB_CHECK_ARG(a->n_runs <= tf::MAX_RUNS, "cb_tp_conv_forward: %d runs (max %d)", a->n_runs, tf::MAX_RUNS);
+    const tf::Layout L = tf::make_layout(H, a->d_out, t.n_slots);
+    const size_t smem = sizeof(float) * (size_t)L.total;
+    CB_CHECK_ARG(smem <= 220 * 1024, "cb_tp_conv_forward: transform kernel needs %zu B of shared memory", smem);
+    cudaError_t e = cudaFuncSetAttribute(tf::tp_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         cb_set_error("cb_tp_conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return CB_ERR_CUDA;
     }
-    const int tiles = cb_div_up(a->node_end - a->node_begin, NB);
-    tp_transform_kernel<<<tiles, TT, smem, st>>>(*a);
+    const int tiles = cb_div_up(a->node_end - a->node_begin, tf::NB);
+    tf::tp_transform_kernel<<<tiles, tf::TT, smem, st>>>(*a);
     CB_CHECK_LAUNCH("cb_tp_conv_forward(transform)");
     return CB_OK;
 }

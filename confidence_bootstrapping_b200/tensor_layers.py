@@ -129,10 +129,26 @@ class TensorProductConvLayer(nn.Module):
                                              dropout, activation) for _ in range(edge_groups)])
         self.batch_norm = EquivariantBatchNorm(out_irreps) if batch_norm else None
         self._dev_prog = None
+        self._w2a_cache = {}
 
     # ------------------------------------------------------------------ helpers
     def _fc(self, g):
         return self.fc if self.edge_groups == 1 else self.fc[g]
+
+    def _w2a(self, g):
+        """Second Linear of the radial MLP with its bias folded in: [weight_numel, H+4] rows (W2[w], b2[w], 0, 0, 0),
+        the layout the transform kernel streams with contiguous bulk copies.  Rebuilt when the parameters change."""
+        W2, b2 = self._fc(g)[3].weight, self._fc(g)[3].bias
+        key = (W2.data_ptr(), W2._version, b2.data_ptr(), b2._version, W2.device)
+        hit = self._w2a_cache.get(g)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                t = torch.zeros(W2.shape[0], W2.shape[1] + 4, device=W2.device, dtype=torch.float32)
+                t[:, :W2.shape[1]] = W2
+                t[:, W2.shape[1]] = b2
+            hit = (key, t)
+            self._w2a_cache[g] = hit
+        return hit[1]
 
     def device_program(self, device):
         if self._dev_prog is None or self._dev_prog.rows.device != device:
@@ -195,7 +211,7 @@ class TensorProductConvLayer(nn.Module):
             prev = key
         for k, s in enumerate(segments):
             fc = self._fc(s.group)
-            W1, b1, W2, b2 = fc[0].weight, fc[0].bias, fc[3].weight, fc[3].bias
+            W1, b1, W2a = fc[0].weight, fc[0].bias, self._w2a(s.group)
             sg = a.segs[k]
             sg.rowptr, sg.col = _lib.i32(s.edges.rowptr, "rowptr"), _lib.i32(s.edges.col, "col")
             sg.e_attr, sg.sh = _lib.f32(s.e_attr, "e_attr"), _lib.f32(s.sh, "sh")
@@ -208,7 +224,7 @@ class TensorProductConvLayer(nn.Module):
                 t, off = P_nbr[s.group]
                 sg.P_nbr, sg.ldp_nbr = t.data_ptr() + 4 * off, t.shape[1]
             sg.W1e, sg.ldw1 = _lib.f32(W1, "W1") + 4 * e_cols[0], W1.shape[1]
-            sg.b1, sg.W2, sg.b2 = _lib.f32(b1, "b1"), _lib.f32(W2, "W2"), _lib.f32(b2, "b2")
+            sg.b1, sg.W2a = _lib.f32(b1, "b1"), _lib.f32(W2a, "W2a")
             sg.n0, sg.n1, sg.col_off, sg.slot = s.n0, s.n1, s.col_off, slot_ids[k]
         if self.batch_norm is not None:
             scale, shift = self.batch_norm.affine()

@@ -141,8 +141,8 @@ typedef struct {
     const float* W1e;       /* first Linear, pointing at the first edge-embedding column [H, ldw1] */
     int32_t ldw1;
     const float* b1;        /* [H]                                                              */
-    const float* W2;        /* [weight_numel, H] second Linear (native layout)                  */
-    const float* b2;        /* [weight_numel]                                                   */
+    const float* W2a;       /* [weight_numel, H+4] second Linear with its bias folded in: row w =
+                               (W2[w][0..H), b2[w], 0, 0, 0) -- contiguous rows feed 1-D bulk copies */
     int32_t n0, n1;         /* aggregation-node range served by this segment                    */
     int32_t col_off;        /* added to col[e] to index x / P_nbr (node tables are concatenated)  */
     int32_t slot;           /* segments with the same slot share (n0,n1), the radial MLP and one accumulator;
@@ -165,8 +165,10 @@ typedef struct {
     const float* residual;  /* [n_out, ld_res] added to the first d_res channels, or NULL        */
     int32_t d_res, ld_res;
     float* out;             /* [n_out, d_out]                                                    */
-    /* workspace for the per-(node, slot) accumulators A[item][n_rows][H+4]; the call processes the
-     * aggregation nodes [node_begin, node_end) and needs cb_tp_conv_items(a) * n_rows * (H+4) floats   */
+    /* workspace for the per-(node, slot) accumulators A[n_rows][H+4], stored per (slot, tile of 32 aggregation
+     * nodes counted from node_begin) row-major over (row, rank of the node among the tile's active nodes) so that
+     * the transform kernel reads a tile's row group with one contiguous bulk copy; the call processes the
+     * aggregation nodes [node_begin, node_end) and needs cb_tp_conv_items(a) * n_rows * (H+4) floats            */
     float* workspace; int64_t workspace_floats;
     int32_t node_begin, node_end;
     int32_t accum_mode;     /* accumulate kernel: 1 = fp32 FFMA register tiles, 2 = tcgen05 3xTF32 with TMEM accumulator */
