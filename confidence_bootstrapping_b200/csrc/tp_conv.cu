@@ -904,6 +904,41 @@ __device__ __forceinline__ void row_fma(const float* const (&ap)[NT], const floa
     }
 }
 
+struct ConsumerCtx {
+    float* sm; const int* items; const int* n_items; uint64_t* full_bar; uint64_t* empty_bar;
+    int stage, a_stage, zero, n_active, HA, a4, nl, kc, lane;
+    int rs; bool mine; int w_off, nvalid, row_begin, row_end, run_rs;
+};
+
+// all row groups of one run (over every active slot) for one consumer thread
+template <int MT>
+__device__ __forceinline__ void run_groups(const ConsumerCtx& c, int& G, float (&acc)[NT][MTMAX]) {
+#pragma unroll 1
+    for (int k = 0; k < c.n_active; ++k) {
+        const int n_act = c.n_items[k];
+        int a_off[NT];      // offset of the thread's nodes inside the A stage, or -1: nodes without edges read zeros
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int rank = c.items[k * NB + c.nl + 8 * j];
+            a_off[j] = rank >= 0 ? (c.rs * n_act + rank) * c.HA : -1;
+        }
+#pragma unroll 1
+        for (int rg = c.row_begin; rg < c.row_end; rg += c.run_rs, ++G) {
+            const int s = G % STAGES;
+            const float* Ab = c.sm + s * c.stage;
+            mbar_wait(&c.full_bar[s], (G / STAGES) & 1);
+            if (c.mine && rg + c.rs < c.row_end) {
+                const float* ap[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) ap[j] = a_off[j] >= 0 ? Ab + a_off[j] : c.sm + c.zero;
+                row_fma<MT>(ap, Ab + c.a_stage + c.w_off, c.HA, c.a4, c.kc, c.nvalid, acc);
+            }
+            __syncwarp();
+            if (c.lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&c.empty_bar[s])) : "memory");
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TT, 1)
 tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
     extern __shared__ __align__(128) float sm[];
@@ -976,117 +1011,87 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
     if (a.n_runs == 0) n_active = 0;
     __syncthreads();
 
-    // ---- group sequence: (active slot k, run ri, row group starting at row rg)
-    struct Iter { int k, ri, rg; };
-    auto advance = [&](Iter& it) {
-        it.rg += run_s[it.ri].rs;
-        if (it.rg >= run_s[it.ri].row_end) {
-            if (++it.ri == a.n_runs) { it.ri = 0; ++it.k; }
-            it.rg = run_s[it.ri].row_begin;
-        }
-    };
-    Iter cur{0, 0, a.n_runs > 0 ? run_s[0].row_begin : 0};
-
+    // ---- group sequence: for every run, for every active slot, the run's rows in groups of run.rs rows.  The
+    // partial sums of a run stay in registers across the slots (they add into the same output channels).
     if (warp == CWARPS) {
-        // ================= producer warp: lane = node of the tile
-#pragma unroll 1
-        for (int G = 0; cur.k < n_active; ++G) {
-            const int s = G % STAGES;
-            mbar_wait(&empty_bar[s], ((G / STAGES) & 1) ^ 1);
-            const RunS& run = run_s[cur.ri];
-            const cb_tp_segment& s0 = a.segs[st.first_seg[active[cur.k]]];
-            const int nrs = min(run.rs, run.row_end - cur.rg);
-            float* Ab = sm + s * L.stage;
-            float* Wb = Ab + L.a_stage;
+        // ================= producer warp
+        if (lane == 0) {
             const uint32_t row_bytes = (uint32_t)HA * 4u;
-            if (lane == 0) {
-                const uint32_t bytes = (uint32_t)nrs * (uint32_t)(n_items_s[cur.k] + run.mul) * row_bytes;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full_bar[s])), "r"(bytes) : "memory");
+            int G = 0;
+#pragma unroll 1
+            for (int ri = 0; ri < a.n_runs; ++ri) {
+                const RunS run = run_s[ri];
+#pragma unroll 1
+                for (int k = 0; k < n_active; ++k) {
+                    const int q = active[k], n_act = n_items_s[k];
+                    const float* w2a = a.segs[st.first_seg[q]].W2a + (size_t)run.w_base0 * HA;
+                    // the tile's active rows are contiguous in the workspace: [row][rank][HA]
+                    const float* ws = a.workspace + (size_t)(st.tile_off[q] + (int)blockIdx.x - st.tile0[q]) * n_rows * WS_TILE * HA;
+#pragma unroll 1
+                    for (int rg = run.row_begin; rg < run.row_end; rg += run.rs, ++G) {
+                        const int s = G % STAGES;
+                        mbar_wait(&empty_bar[s], ((G / STAGES) & 1) ^ 1);
+                        const int nrs = min(run.rs, run.row_end - rg);
+                        float* Ab = sm + s * L.stage;
+                        const uint32_t a_bytes = (uint32_t)(nrs * n_act) * row_bytes, w_bytes = (uint32_t)(nrs * run.mul) * row_bytes;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full_bar[s])), "r"(a_bytes + w_bytes)
+                                     : "memory");
+                        bulk_g2s(Ab, ws + (size_t)rg * n_act * HA, a_bytes, &full_bar[s]);
+                        bulk_g2s(Ab + L.a_stage, w2a + (size_t)(rg - run.row_begin) * run.mul * HA, w_bytes, &full_bar[s]);
+                    }
+                }
             }
-            __syncwarp();
-            if (lane == 0) {
-                // the tile's active rows of the group are contiguous in the workspace: [row][rank][HA]
-                const int q = active[cur.k], n_act = n_items_s[cur.k];
-                const float* src = a.workspace + ((size_t)(st.tile_off[q] + (int)blockIdx.x - st.tile0[q]) * n_rows * WS_TILE + (size_t)cur.rg * n_act) * HA;
-                bulk_g2s(Ab, src, (uint32_t)(nrs * n_act) * row_bytes, &full_bar[s]);
-                const int wrow0 = run.w_base0 + (cur.rg - run.row_begin) * run.mul;
-                bulk_g2s(Wb, s0.W2a + (size_t)wrow0 * HA, (uint32_t)(nrs * run.mul) * row_bytes, &full_bar[s]);
-            }
-            advance(cur);
         }
     } else {
         // ================= consumer warps
         const int nl = lane & 7, combo = warp / WPC, kc = (warp % WPC) * 4 + (lane >> 3);
-        const float* zrow = sm + L.zero;
         float acc[NT][MTMAX];
 #pragma unroll
         for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int m = 0; m < MTMAX; ++m) acc[j][m] = 0.0f;
-        int rank[NT] = {-1, -1, -1, -1};
-        int has_k = -1, n_act = 0;
+        int G = 0;
 #pragma unroll 1
-        for (int G = 0; cur.k < n_active; ++G) {
-            const int s = G % STAGES;
-            if (cur.k != has_k) {
-                has_k = cur.k;
-#pragma unroll
-                for (int j = 0; j < NT; ++j) rank[j] = items[cur.k * NB + nl + 8 * j];
-                n_act = n_items_s[cur.k];
-            }
-            const RunS run = run_s[cur.ri];
-            const int nrs = min(run.rs, run.row_end - cur.rg);
-            const float* Ab = sm + s * L.stage;
-            const float* Wb = Ab + L.a_stage;
+        for (int ri = 0; ri < a.n_runs; ++ri) {
+            const RunS run = run_s[ri];
             // combo -> (row of the group, first output of the thread tile)
             const int rs = run.rs == 2 ? combo : 0;
             const int m0 = run.rs == 2 ? 0 : combo * run.mt;
-            mbar_wait(&full_bar[s], (G / STAGES) & 1);
-            if (rs < nrs && m0 < run.mul) {
-                const float* ap[NT];
-#pragma unroll
-                for (int j = 0; j < NT; ++j) ap[j] = rank[j] >= 0 ? Ab + (rs * n_act + rank[j]) * HA : zrow;   // nodes without edges read zeros
-                const float* wp = Wb + (rs * run.mul + m0) * HA;
-                const int nvalid = run.mul - m0;
-                switch (run.mt) {
-                    case 2: row_fma<2>(ap, wp, HA, a4, kc, nvalid, acc); break;
-                    case 4: row_fma<4>(ap, wp, HA, a4, kc, nvalid, acc); break;
-                    case 6: row_fma<6>(ap, wp, HA, a4, kc, nvalid, acc); break;
-                    case 8: row_fma<8>(ap, wp, HA, a4, kc, nvalid, acc); break;
-                    case 12: row_fma<12>(ap, wp, HA, a4, kc, nvalid, acc); break;
-                    default: row_fma<16>(ap, wp, HA, a4, kc, nvalid, acc); break;
-                }
+            const ConsumerCtx cx{sm, items, n_items_s, full_bar, empty_bar, L.stage, L.a_stage, L.zero, n_active, HA, a4, nl, kc, lane,
+                                 rs, m0 < run.mul, (rs * run.mul + m0) * HA, run.mul - m0, run.row_begin, run.row_end, run.rs};
+            switch (run.mt) {
+                case 2: run_groups<2>(cx, G, acc); break;
+                case 4: run_groups<4>(cx, G, acc); break;
+                case 6: run_groups<6>(cx, G, acc); break;
+                case 8: run_groups<8>(cx, G, acc); break;
+                case 12: run_groups<12>(cx, G, acc); break;
+                default: run_groups<16>(cx, G, acc); break;
             }
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
-            if (cur.rg + run.rs >= run.row_end) {
-                // ---- end of the run: reduce the partial sums in a fixed order and add into the output channels
-                asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");   // the previous run's reducers are done with `part`
+            // ---- end of the run: reduce the partial sums in a fixed order and add into the output channels
+            asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");   // the previous run's reducers are done with `part`
 #pragma unroll
-                for (int j = 0; j < NT; ++j)
+            for (int j = 0; j < NT; ++j)
 #pragma unroll
-                    for (int m = 0; m < MTMAX; ++m) {
-                        if (m < run.mt) {       // uniform
-                            float v = acc[j][m];
-                            v += __shfl_xor_sync(0xffffffffu, v, 8);
-                            v += __shfl_xor_sync(0xffffffffu, v, 16);
-                            if (lane < 8) part[((warp * 8 + nl) * NT + j) * MTMAX + m] = v;
-                        }
-                        acc[j][m] = 0.0f;
+                for (int m = 0; m < MTMAX; ++m) {
+                    if (m < run.mt) {       // uniform
+                        float v = acc[j][m];
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if (lane < 8) part[((warp * 8 + nl) * NT + j) * MTMAX + m] = v;
                     }
-                asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
-#pragma unroll 1
-                for (int i = tid; i < NB * run.mul; i += CT) {
-                    const int m = i % run.mul, n = i / run.mul;
-                    const int c_lo = run.rs == 2 ? 0 : m / run.mt, c_hi = run.rs == 2 ? 2 : c_lo + 1;
-                    const int mm = run.rs == 2 ? m : m - c_lo * run.mt;
-                    float v = 0.0f;
-#pragma unroll 1
-                    for (int w = c_lo * WPC; w < c_hi * WPC; ++w) v += part[((w * 8 + (n & 7)) * NT + (n >> 3)) * MTMAX + mm];
-                    outacc[n * d_out + run.out_base + m * run.out_step] += v;
+                    acc[j][m] = 0.0f;
                 }
+            asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
+#pragma unroll 1
+            for (int i = tid; i < NB * run.mul; i += CT) {
+                const int m = i % run.mul, n = i / run.mul;
+                const int c_lo = run.rs == 2 ? 0 : m / run.mt, c_hi = run.rs == 2 ? 2 : c_lo + 1;
+                const int mm = run.rs == 2 ? m : m - c_lo * run.mt;
+                float v = 0.0f;
+#pragma unroll 1
+                for (int w = c_lo * WPC; w < c_hi * WPC; ++w) v += part[((w * 8 + (n & 7)) * NT + (n >> 3)) * MTMAX + mm];
+                outacc[n * d_out + run.out_base + m * run.out_step] += v;
             }
-            advance(cur);
         }
     }
     __syncthreads();
