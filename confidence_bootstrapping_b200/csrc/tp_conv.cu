@@ -353,6 +353,10 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
 }
 
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, int sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -376,14 +380,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 struct Layout {
-    int rows, terms, w1e, hbase, cols, xs, shs, es, ps, fhi, flo, hhi, hlo, total;  // byte offsets
-    int nep, dxp, npad, mtiles;
+    int rows, terms, hbase, cols, xs, shs, es, ps, fhi, flo, hhi, hlo, w1hi, w1lo, ehi, elo, total;  // byte offsets
+    int dxp, npad, mtiles, sbow;
 };
 
 __host__ __device__ inline Layout make_layout(int n_rows, int n_terms, int ne, int d_in, int S, int H) {
     Layout L;
     auto al = [](int v, int a) { return (v + a - 1) / a * a; };
-    L.nep = ne + 4;
+    L.sbow = (ne / 4) * LBO;     // stride between 8-row groups of the [.., ne] operand tiles of the hidden-layer MMA
     L.dxp = d_in + (d_in & 1);   // even: rows are filled with 8-byte cp.async
     L.npad = al(H + 1, 16);
     L.mtiles = (n_rows + 127) / 128;
@@ -392,9 +396,12 @@ __host__ __device__ inline Layout make_layout(int n_rows, int n_terms, int ne, i
     L.flo = o;   o += L.mtiles * 16 * SBO;
     L.hhi = o;   o += (L.npad / 8) * SBO;
     L.hlo = o;   o += (L.npad / 8) * SBO;
+    L.ehi = o;   o += (KC / 8) * L.sbow;
+    L.elo = o;   o += (KC / 8) * L.sbow;
+    L.w1hi = o;  o += ((H + 7) / 8) * L.sbow;     // the MMA reads 128 rows: rows >= H overlap what follows and only
+    L.w1lo = o;  o += ((H + 7) / 8) * L.sbow;     // feed accumulator lanes that are never read back
     L.rows = o;  o += al(n_rows * 32, 16);
     L.terms = o; o += al(n_terms * 8, 16);
-    L.w1e = o;   o += al(H * L.nep * 4, 16);
     L.hbase = o; o += al(H * 4, 16);
     L.cols = o;  o += al(2 * KC * 4, 16);          // raw-operand staging is double buffered
     L.xs = o;    o += al(2 * KC * L.dxp * 4, 16);
@@ -426,17 +433,20 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int H = a.H, ne = a.ne, S = a.S, d_in = a.d_in, n_rows = a.n_rows;
     const Layout L = make_layout(n_rows, a.n_terms, ne, d_in, S, H);
-    const int nep = L.nep, dxp = L.dxp, NP = L.npad, MT = L.mtiles, HA = H + PADC;
+    const int dxp = L.dxp, NP = L.npad, MT = L.mtiles, HA = H + PADC, SBOW = L.sbow;
     unsigned char* Fhi = smraw + L.fhi;
     unsigned char* Flo = smraw + L.flo;
     unsigned char* Hhi = smraw + L.hhi;
     unsigned char* Hlo = smraw + L.hlo;
     cb_tp_row* rows_s = reinterpret_cast<cb_tp_row*>(smraw + L.rows);
     cb_tp_term* terms_s = reinterpret_cast<cb_tp_term*>(smraw + L.terms);
-    float* W1e_s = reinterpret_cast<float*>(smraw + L.w1e);
+    unsigned char* W1hi = smraw + L.w1hi;
+    unsigned char* W1lo = smraw + L.w1lo;
+    unsigned char* Ehi = smraw + L.ehi;
+    unsigned char* Elo = smraw + L.elo;
     float* hbase = reinterpret_cast<float*>(smraw + L.hbase);
     __shared__ SlotTable st;
-    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t mma_bar, h_bar;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -451,6 +461,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     if (tid == 0) {
         build_slots(a, st);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&h_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -476,7 +487,10 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_h = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t tmem_h = tmem_base + (uint32_t)(MT * NP);   // [128 hidden lanes] x [KC edge columns] pre-activations
     uint32_t commits = 0, waited = 0;   // block-uniform bookkeeping of the MMA barrier phases
+    uint32_t h_phase = 0;
     int staged_slot = -1;
     // terms of the thread's (first) f-row live in registers; rows beyond THREADS use the generic loop
     constexpr int MAXT = 4;
@@ -495,6 +509,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         t_cf[t] = on ? tm.coef : 0.0f;
     }
     const uint32_t fhi_a = smem_u32(Fhi), flo_a = smem_u32(Flo), hhi_a = smem_u32(Hhi), hlo_a = smem_u32(Hlo);
+    const uint32_t w1hi_a = smem_u32(W1hi), w1lo_a = smem_u32(W1lo), ehi_a = smem_u32(Ehi), elo_a = smem_u32(Elo);
 
     // ---- chunk iterator (block-uniform): items of this CTA in increasing order, their segments, KC edges at a time
     auto seg_range = [&](int seg, int node, int& e0, int& e1) {
@@ -601,13 +616,19 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             const cb_tp_segment& s0 = a.segs[st.first_seg[cur.q]];
             if (staged_slot != cur.q) {
 #pragma unroll 1
-                for (int i = tid; i < H * (ne / 4); i += THREADS) {
+                for (int i = tid; i < H * (ne / 4); i += THREADS) {   // hi/lo operand tiles of W1e: row = hidden unit, K = edge channel
                     const int qq = i / (ne / 4), c4 = i - qq * (ne / 4);
-                    *reinterpret_cast<float4*>(W1e_s + qq * nep + 4 * c4) =
-                        __ldg(reinterpret_cast<const float4*>(s0.W1e + (size_t)qq * s0.ldw1) + c4);
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(s0.W1e + (size_t)qq * s0.ldw1) + c4);
+                    float4 hi, lo;
+                    split_tf32(w.x, hi.x, lo.x);
+                    split_tf32(w.y, hi.y, lo.y);
+                    split_tf32(w.z, hi.z, lo.z);
+                    split_tf32(w.w, hi.w, lo.w);
+                    const int off = (qq >> 3) * SBOW + c4 * LBO + (qq & 7) * 16;
+                    *reinterpret_cast<float4*>(W1hi + off) = hi;
+                    *reinterpret_cast<float4*>(W1lo + off) = lo;
                 }
                 staged_slot = cur.q;
-                __syncthreads();
             }
             const int graph = a.agg_graph ? a.agg_graph[cur.node] : 0;
 #pragma unroll 1
@@ -617,7 +638,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 if (s0.e_post) {
                     const float* ep = s0.e_post + (size_t)graph * ne;
 #pragma unroll 4
-                    for (int c = 0; c < ne; ++c) v = fmaf(W1e_s[qq * nep + c], ep[c], v);
+                    for (int c = 0; c < ne; ++c) v = fmaf(__ldg(s0.W1e + (size_t)qq * s0.ldw1 + c), ep[c], v);
                 }
                 hbase[qq] = v;
             }
@@ -634,6 +655,35 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         const float* shs = shs_of(buf);
         const float* es = es_of(buf);
         const float* Ps = ps_of(buf);
+        const int ksteps = (n + 7) >> 3;
+        // ---- hidden layer on the tensor core: pre[q][e] = sum_c W1e[q][c] * e_attr[e][c]  (M = 128 hidden lanes,
+        // N = KC edges, K = ne, 3xTF32); the edge-embedding rows of the chunk become the hi/lo B-operand tiles
+#pragma unroll 1
+        for (int i = tid; i < KC * (ne / 4); i += THREADS) {
+            const int e = i / (ne / 4), c4 = i - e * (ne / 4);
+            const float4 v = *reinterpret_cast<const float4*>(es + e * ne + 4 * c4);   // rows >= n hold stale data: zeroed after the MMA
+            float4 hi, lo;
+            split_tf32(v.x, hi.x, lo.x);
+            split_tf32(v.y, hi.y, lo.y);
+            split_tf32(v.z, hi.z, lo.z);
+            split_tf32(v.w, hi.w, lo.w);
+            const int off = (e >> 3) * SBOW + c4 * LBO + (e & 7) * 16;
+            *reinterpret_cast<float4*>(Ehi + off) = hi;
+            *reinterpret_cast<float4*>(Elo + off) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int ks = 0; ks < ne / 8; ++ks) {
+                const uint32_t ko = (uint32_t)(ks * 2 * LBO);
+                mma_tf32(tmem_h, make_desc_sbo(w1hi_a + ko, SBOW), make_desc_sbo(ehi_a + ko, SBOW), idesc_h, ks > 0 ? 1u : 0u);
+                mma_tf32(tmem_h, make_desc_sbo(w1hi_a + ko, SBOW), make_desc_sbo(elo_a + ko, SBOW), idesc_h, 1u);
+                mma_tf32(tmem_h, make_desc_sbo(w1lo_a + ko, SBOW), make_desc_sbo(ehi_a + ko, SBOW), idesc_h, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&h_bar)) : "memory");
+        }
         // ---- F^T tile: row r = f-row, column = edge; hi/lo TF32 split.  Loops stay rolled on purpose:
         // the kernel must fit the 32 KB instruction cache (an unrolled build stalled on instruction fetch).
         const int nq = 2 * ((n + 7) >> 3);   // 4-edge groups covered by the MMA k-steps of this chunk
@@ -701,54 +751,55 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
             }
         }
-        // ---- H~ tile: row q = hidden unit (row H = constant 1), column = edge
-#pragma unroll 1
-        for (int i = tid; i < (H + 1) * 2; i += THREADS) {
-            const int qq = i >> 1, half = i & 1;
-            const float4* w4 = reinterpret_cast<const float4*>(W1e_s + qq * nep);
-            const int rbase = (qq >> 3) * SBO + (qq & 7) * 16;
-#pragma unroll 1
-            for (int e4 = half; e4 < nq; e4 += 2) {
-                float v[4];
+        // ---- H~ tile: row q = hidden unit (row H = constant 1), column = edge.  The pre-activations come back from
+        // TMEM one hidden unit per lane (warps 0-3: edges 0-7, warps 4-7: edges 8-15) -- exactly one row of the
+        // K-major operand tile -- and get the node / neighbour projections, the ReLU and the hi/lo split.
+        mbar_wait(&h_bar, h_phase);
+        h_phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const int qq = (warp & 3) * 32 + lane, eh = warp >> 2;
+            if (eh < ksteps) {     // warp-uniform
+                uint32_t v[8];
+                const uint32_t taddr = tmem_h + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * eh);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (qq < NP) {
+                    float h[8];
+                    if (qq < H) {
+                        const float hb = hbase[qq];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int e = 4 * e4 + j;
-                    float acc = 0.0f;
-                    if (e < n) {
-                        if (qq == H) {
-                            acc = 1.0f;
-                        } else {
-                            acc = hbase[qq];
-                            if (sg.P_nbr) acc += Ps[e * H + qq];
-                            const float4* ev = reinterpret_cast<const float4*>(es + e * ne);
-#pragma unroll 2
-                            for (int c = 0; c < ne / 4; ++c) {
-                                const float4 w = w4[c], x4 = ev[c];
-                                acc = fmaf(w.x, x4.x, acc);
-                                acc = fmaf(w.y, x4.y, acc);
-                                acc = fmaf(w.z, x4.z, acc);
-                                acc = fmaf(w.w, x4.w, acc);
-                            }
-                            acc = fmaxf(acc, 0.0f);
+                        for (int j = 0; j < 8; ++j) {
+                            float pre = __uint_as_float(v[j]) + hb;
+                            if (sg.P_nbr) pre += Ps[(8 * eh + j) * H + qq];
+                            h[j] = 8 * eh + j < n ? fmaxf(pre, 0.0f) : 0.0f;
                         }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h[j] = qq == H ? 1.0f : 0.0f;
                     }
-                    v[j] = acc;
+                    const int rbase = (qq >> 3) * SBO + (qq & 7) * 16 + 2 * eh * LBO;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        float4 hi, lo;
+                        split_tf32(h[4 * g + 0], hi.x, lo.x);
+                        split_tf32(h[4 * g + 1], hi.y, lo.y);
+                        split_tf32(h[4 * g + 2], hi.z, lo.z);
+                        split_tf32(h[4 * g + 3], hi.w, lo.w);
+                        *reinterpret_cast<float4*>(Hhi + rbase + g * LBO) = hi;
+                        *reinterpret_cast<float4*>(Hlo + rbase + g * LBO) = lo;
+                    }
                 }
-                float4 hi, lo;
-                split_tf32(v[0], hi.x, lo.x);
-                split_tf32(v[1], hi.y, lo.y);
-                split_tf32(v[2], hi.z, lo.z);
-                split_tf32(v[3], hi.w, lo.w);
-                *reinterpret_cast<float4*>(Hhi + rbase + e4 * LBO) = hi;
-                *reinterpret_cast<float4*>(Hlo + rbase + e4 * LBO) = lo;
             }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
         __syncthreads();
         // ---- one thread issues the MMAs of this chunk and commits them to the barrier
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int ksteps = (n + 7) >> 3;
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
                 const uint32_t d = tmem_base + (uint32_t)(mt * NP);
@@ -776,9 +827,10 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             int row_stride;
             float* Aout = a.workspace + ws_place(a, st, cur.q, cur.node, n_rows, HA, lane, row_stride);
             const int lg = warp & 3;                 // TMEM lane group this warp may access
+            constexpr int STG_LD = 36;               // floats per staged row: 144-byte stride keeps float4 accesses conflict-free
+            float* stg = reinterpret_cast<float*>(smraw + L.fhi) + warp * 32 * STG_LD;
 #pragma unroll 1
             for (int mt = warp >> 2; mt < MT; mt += THREADS / 128) {
-                const int r = mt * 128 + lg * 32 + lane;
 #pragma unroll 1
                 for (int c0 = 0; c0 < NP; c0 += 32) {   // NP is a multiple of 16; a trailing half chunk reads 16 spare columns
                     uint32_t v[32];
@@ -795,14 +847,23 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                             : "r"(taddr + 16u));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (r < n_rows) {
-                        float* dst = Aout + (size_t)r * row_stride + c0;
+                    // transpose the warp's 32 rows x 32 columns through shared memory (the operand tiles are idle
+                    // here) so that 8 lanes write 128 contiguous bytes of one row instead of 32 lanes hitting 32 rows
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (c0 + j < HA)
-                                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(stg + lane * STG_LD + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    __syncwarp();
+                    const int sub = lane >> 3, ch = (lane & 7) * 4;
+                    if (c0 + ch < HA) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rl = 4 * i + sub, rr = mt * 128 + lg * 32 + rl;
+                            if (rr < n_rows)
+                                *reinterpret_cast<float4*>(Aout + (size_t)rr * row_stride + c0 + ch) = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ch);
+                        }
                     }
+                    __syncwarp();
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1174,8 +1235,9 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
         int rc;
         if (a->accum_mode == 2) {
             CB_CHECK_ARG(a->d_in % 2 == 0, "cb_tp_conv_forward: tcgen05 accumulate needs an even node-feature width (d_in=%d)", a->d_in);
-            CB_CHECK_ARG(R <= 384 && ((R + 127) / 128) * ((H + 1 + 15) / 16 * 16) <= tc::TMEM_COLS,
+            CB_CHECK_ARG(R <= 384 && ((R + 127) / 128) * ((H + 1 + 15) / 16 * 16) + tc::KC <= tc::TMEM_COLS,
                          "cb_tp_conv_forward: tcgen05 accumulate supports rows<=384 and tiles within 256 TMEM columns (rows=%d H=%d)", R, H);
+            CB_CHECK_ARG(a->ne % 8 == 0 && H <= 120, "cb_tp_conv_forward: tcgen05 accumulate needs ne %% 8 == 0 and H <= 120 (ne=%d H=%d)", a->ne, H);
             const tc::Layout L = tc::make_layout(R, a->n_terms, a->ne, a->d_in, a->S, H);
             // at least 80 KB so that never more than 2 CTAs (2 x 256 TMEM columns) share an SM
             const size_t smem = (size_t)(L.total > 80 * 1024 ? L.total : 80 * 1024);

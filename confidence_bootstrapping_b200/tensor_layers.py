@@ -240,7 +240,8 @@ class TensorProductConvLayer(nn.Module):
         per_item = P.n_rows * (H + 4)
         a.node_begin, a.node_end = 0, n_out
         np_cols = -(-(H + 1) // 16) * 16
-        tc_ok = P.n_rows <= 384 and -(-P.n_rows // 128) * np_cols <= 256 and x.shape[1] % 2 == 0
+        tc_ok = (P.n_rows <= 384 and -(-P.n_rows // 128) * np_cols + 16 <= 256 and x.shape[1] % 2 == 0
+                 and e_cols[1] % 8 == 0 and H <= 120)
         a.accum_mode = ACCUM_MODE if tc_ok else 1
         items = _lib.tp_conv_items(a)
         max_items = max(1, WORKSPACE_BYTES // (4 * per_item))
