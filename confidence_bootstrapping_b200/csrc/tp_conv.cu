@@ -428,6 +428,52 @@ __device__ __forceinline__ void cp_async_bytes16(void* smem_dst, const void* gsr
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
 }
 
+constexpr int MAXT = 4;   // terms of a thread's f-row kept in registers
+
+struct FRowCtx {
+    const float* xs; const float* shs; const cb_tp_term* terms_s; unsigned char* Fhi; unsigned char* Flo;
+    int dxp, S, n, nq, tb0, te0, rbase;
+};
+
+// F^T tile row of one thread: F[r][e] = sum_t coef_t * x[col e][xi_t] * sh_e[si_t] for the chunk's edges, hi/lo split,
+// four consecutive edges per 16-byte core-matrix row.  NT = register-resident terms evaluated (warp-uniform).
+template <int NT>
+__device__ __forceinline__ void f_row(const FRowCtx& c, const int (&t_xi)[MAXT], const int (&t_si)[MAXT], const float (&t_cf)[MAXT]) {
+#pragma unroll 1
+    for (int e4 = 0; e4 < c.nq; ++e4) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = min(4 * e4 + j, c.n - 1);          // clamp: edges >= n are zeroed below
+            const float* xe = c.xs + e * c.dxp;
+            const float* se = c.shs + e * c.S;
+            float acc = 0.0f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc = fmaf(t_cf[t] * xe[t_xi[t]], se[t_si[t]], acc);
+            v[j] = (4 * e4 + j < c.n) ? acc : 0.0f;
+        }
+        if (c.te0 - c.tb0 > MAXT) {   // rare long rows: finish from the shared-memory term table
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = 4 * e4 + j;
+                if (e < c.n)
+#pragma unroll 1
+                    for (int t = c.tb0 + MAXT; t < c.te0; ++t) {
+                        const cb_tp_term tm = c.terms_s[t];
+                        v[j] = fmaf(tm.coef * c.xs[e * c.dxp + tm.x_idx], c.shs[e * c.S + tm.sh_idx], v[j]);
+                    }
+            }
+        }
+        float4 hi, lo;
+        split_tf32(v[0], hi.x, lo.x);
+        split_tf32(v[1], hi.y, lo.y);
+        split_tf32(v[2], hi.z, lo.z);
+        split_tf32(v[3], hi.w, lo.w);
+        *reinterpret_cast<float4*>(c.Fhi + c.rbase + e4 * LBO) = hi;   // 4 consecutive edges = one 16-byte core-matrix row
+        *reinterpret_cast<float4*>(c.Flo + c.rbase + e4 * LBO) = lo;
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 2)
 tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -493,7 +539,6 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     uint32_t h_phase = 0;
     int staged_slot = -1;
     // terms of the thread's (first) f-row live in registers; rows beyond THREADS use the generic loop
-    constexpr int MAXT = 4;
     int tb0 = 0, te0 = 0, t_xi[MAXT], t_si[MAXT];
     float t_cf[MAXT];
     if (tid < n_rows) {
@@ -508,8 +553,13 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         t_si[t] = tm.sh_idx;
         t_cf[t] = on ? tm.coef : 0.0f;
     }
+    // number of register-resident terms the warp's rows need (warp-uniform)
+    const int nt_warp = __reduce_max_sync(0xffffffffu, min(te0 - tb0, MAXT));
     const uint32_t fhi_a = smem_u32(Fhi), flo_a = smem_u32(Flo), hhi_a = smem_u32(Hhi), hlo_a = smem_u32(Hlo);
-    const uint32_t w1hi_a = smem_u32(W1hi), w1lo_a = smem_u32(W1lo), ehi_a = smem_u32(Ehi), elo_a = smem_u32(Elo);
+    const uint64_t d_fhi = make_desc(fhi_a), d_flo = make_desc(flo_a), d_hhi = make_desc(hhi_a), d_hlo = make_desc(hlo_a);
+    const uint64_t d_w1hi = make_desc_sbo(smem_u32(W1hi), SBOW), d_w1lo = make_desc_sbo(smem_u32(W1lo), SBOW);
+    const uint64_t d_ehi = make_desc_sbo(smem_u32(Ehi), SBOW), d_elo = make_desc_sbo(smem_u32(Elo), SBOW);
+    static_assert(KC == 16, "the MMA issue code is written for two k-steps per chunk");
 
     // ---- chunk iterator (block-uniform): items of this CTA in increasing order, their segments, KC edges at a time
     auto seg_range = [&](int seg, int node, int& e0, int& e1) {
@@ -675,12 +725,14 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
+            // descriptors differ only in the start-address field: advance it by one k-step (2 core matrices) per iteration
+            uint64_t dwh = d_w1hi, dwl = d_w1lo, deh = d_ehi, del = d_elo;
+#pragma unroll 2
             for (int ks = 0; ks < ne / 8; ++ks) {
-                const uint32_t ko = (uint32_t)(ks * 2 * LBO);
-                mma_tf32(tmem_h, make_desc_sbo(w1hi_a + ko, SBOW), make_desc_sbo(ehi_a + ko, SBOW), idesc_h, ks > 0 ? 1u : 0u);
-                mma_tf32(tmem_h, make_desc_sbo(w1hi_a + ko, SBOW), make_desc_sbo(elo_a + ko, SBOW), idesc_h, 1u);
-                mma_tf32(tmem_h, make_desc_sbo(w1lo_a + ko, SBOW), make_desc_sbo(ehi_a + ko, SBOW), idesc_h, 1u);
+                mma_tf32(tmem_h, dwh, deh, idesc_h, ks > 0 ? 1u : 0u);
+                mma_tf32(tmem_h, dwh, del, idesc_h, 1u);
+                mma_tf32(tmem_h, dwl, deh, idesc_h, 1u);
+                dwh += (2 * LBO) >> 4; dwl += (2 * LBO) >> 4; deh += (2 * LBO) >> 4; del += (2 * LBO) >> 4;
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&h_bar)) : "memory");
         }
@@ -688,39 +740,12 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         // the kernel must fit the 32 KB instruction cache (an unrolled build stalled on instruction fetch).
         const int nq = 2 * ((n + 7) >> 3);   // 4-edge groups covered by the MMA k-steps of this chunk
         if (tid < n_rows) {
-            const int rbase = (tid >> 3) * SBO + (tid & 7) * 16;
-#pragma unroll 1
-            for (int e4 = 0; e4 < nq; ++e4) {
-                float v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int e = min(4 * e4 + j, n - 1);          // clamp: edges >= n are zeroed below
-                    const float* xe = xs + e * dxp;
-                    const float* se = shs + e * S;
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int t = 0; t < MAXT; ++t) acc = fmaf(t_cf[t] * xe[t_xi[t]], se[t_si[t]], acc);
-                    v[j] = (4 * e4 + j < n) ? acc : 0.0f;
-                }
-                if (te0 - tb0 > MAXT) {   // rare long rows: finish from the shared-memory term table
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int e = 4 * e4 + j;
-                        if (e < n)
-#pragma unroll 1
-                            for (int t = tb0 + MAXT; t < te0; ++t) {
-                                const cb_tp_term tm = terms_s[t];
-                                v[j] = fmaf(tm.coef * xs[e * dxp + tm.x_idx], shs[e * S + tm.sh_idx], v[j]);
-                            }
-                    }
-                }
-                float4 hi, lo;
-                split_tf32(v[0], hi.x, lo.x);
-                split_tf32(v[1], hi.y, lo.y);
-                split_tf32(v[2], hi.z, lo.z);
-                split_tf32(v[3], hi.w, lo.w);
-                *reinterpret_cast<float4*>(Fhi + rbase + e4 * LBO) = hi;   // 4 consecutive edges = one 16-byte core-matrix row
-                *reinterpret_cast<float4*>(Flo + rbase + e4 * LBO) = lo;
+            const FRowCtx fc{xs, shs, terms_s, Fhi, Flo, dxp, S, n, nq, tb0, te0, (tid >> 3) * SBO + (tid & 7) * 16};
+            switch (nt_warp) {      // warp-uniform: most f-rows have a single term
+                case 1: f_row<1>(fc, t_xi, t_si, t_cf); break;
+                case 2: f_row<2>(fc, t_xi, t_si, t_cf); break;
+                case 3: f_row<3>(fc, t_xi, t_si, t_cf); break;
+                default: f_row<MAXT>(fc, t_xi, t_si, t_cf); break;
             }
         }
 #pragma unroll 1
@@ -803,14 +828,16 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
                 const uint32_t d = tmem_base + (uint32_t)(mt * NP);
-                uint32_t acc = cur.first ? 0u : 1u;
-#pragma unroll 1
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint32_t ao = (uint32_t)(mt * 16 * SBO + ks * 2 * LBO), bo = (uint32_t)(ks * 2 * LBO);
-                    mma_tf32(d, make_desc(fhi_a + ao), make_desc(hhi_a + bo), idesc, acc);
-                    mma_tf32(d, make_desc(fhi_a + ao), make_desc(hlo_a + bo), idesc, 1u);
-                    mma_tf32(d, make_desc(flo_a + ao), make_desc(hhi_a + bo), idesc, 1u);
-                    acc = 1u;
+                const uint32_t acc0 = cur.first ? 0u : 1u;
+                uint64_t dfh = d_fhi + (uint64_t)((mt * 16 * SBO) >> 4), dfl = d_flo + (uint64_t)((mt * 16 * SBO) >> 4);
+                mma_tf32(d, dfh, d_hhi, idesc, acc0);
+                mma_tf32(d, dfh, d_hlo, idesc, 1u);
+                mma_tf32(d, dfl, d_hhi, idesc, 1u);
+                if (ksteps > 1) {
+                    dfh += (2 * LBO) >> 4; dfl += (2 * LBO) >> 4;
+                    mma_tf32(d, dfh, d_hhi + ((2 * LBO) >> 4), idesc, 1u);
+                    mma_tf32(d, dfh, d_hlo + ((2 * LBO) >> 4), idesc, 1u);
+                    mma_tf32(d, dfl, d_hhi + ((2 * LBO) >> 4), idesc, 1u);
                 }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
