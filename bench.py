@@ -34,8 +34,9 @@ def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
-    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1590.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -154,6 +155,11 @@ def workload_config(confidence):
 
 
 # ----------------------------------------------------------------------------------------- cb200 arm
+# dram__bytes_read.sum + dram__bytes_write.sum of the two K3 kernels for the 74->74 conv layer of the bench workload
+# (ncu --set full, profiles/r1/k3_ncu_summary.txt); refreshed whenever the kernels change
+K3_DRAM_BYTES_PER_CALL = None
+
+
 class TpTimer:
     """CUDA-event timing + algorithmic byte/FLOP accounting of every K3 launch in the timed region."""
 
@@ -183,7 +189,9 @@ class TpTimer:
             tot_bytes += 4.0 * (meta["n_in"] * d_in + meta["n_out"] * d_out) + sum(E) * (4.0 * ne + 4.0 * S + 8.0) + 4.0 * params
             slots = layer.program.n_slots
             tot_flops_ref += sum(E) * 2.0 * (K1 * H + H * numel + slots)
-            tot_flops_exec += sum(E) * 2.0 * (ne * H + R * (H + 1)) + 2.0 * meta["n_out"] * len(E) * slots * (H + 1)
+            # executed: per edge the hidden layer + R x (H+1) rank-1 update (a 3xTF32 product counted once), per
+            # (node, edge group) the numel x (H+1) transform (upper bound: pairs without edges are skipped)
+            tot_flops_exec += sum(E) * 2.0 * (ne * H + R * (H + 1)) + 2.0 * meta["n_out"] * len(meta["groups"]) * numel * (H + 1)
             tot_ms += s.elapsed_time(e)
             n += 1
         return dict(launches=n, ms=tot_ms, bytes=tot_bytes, flops_ref=tot_flops_ref, flops_exec=tot_flops_exec)
@@ -194,6 +202,7 @@ def run_cb200(opts):
     from confidence_bootstrapping_b200 import _lib
     from confidence_bootstrapping_b200 import dist as cbdist
     from confidence_bootstrapping_b200.configs import confidence_model_args, score_model_args
+    from confidence_bootstrapping_b200 import data as cbdata
     from confidence_bootstrapping_b200.data import Batch
     from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule, t_to_sigma
     from confidence_bootstrapping_b200.sampling import _mask_rotate_of, reverse_diffusion, sampling
@@ -227,13 +236,15 @@ def run_cb200(opts):
         dl = build_workload(seed, args_ns, SAMPLES)
         fl = copy.deepcopy(dl) if conf_model is not None else None
         torch.cuda.synchronize()
+        h2d0 = cbdata.H2D_BYTES
         t0 = time.perf_counter()
         out, conf = sampling(data_list=dl, confidence_model=conf_model, filtering_data_list=fl, filtering_model_args=conf_args, **kw)
         poses = torch.stack([d["ligand"].pos for d in out]).cpu()
         c = conf.cpu() if conf is not None else None
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        h2d = host_bytes(dl) + (host_bytes(fl) if fl is not None else 0)
+        # bytes that actually crossed the bus: the collate-to-device path sends attributes shared by the N copies once
+        h2d = cbdata.H2D_BYTES - h2d0
         d2h = poses.numel() * 4 + (c.numel() * 4 if c is not None else 0)
         return dt, h2d, d2h
 
@@ -305,14 +316,25 @@ def run_cb200(opts):
                     "d2h_bytes_per_step": int(e2e[0][2])},
         }
         if tp["launches"]:
-            gbs = tp["bytes"] / (tp["ms"] * 1e-3) / 1e9
-            out["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                               "traffic": None, "kernel": "tp_conv_kernel (K3, all launches of the timed region)",
-                               "peak_source": peaks["source"], "launches": tp["launches"],
-                               "avg_launch_ms": tp["ms"] / tp["launches"], "share_of_step": tp["ms"] / (ms_step * opts.steps),
+            # K3: compute-bound on the tensor pipe.  achieved = algorithmic FLOPs of the REFERENCE formulation
+            # (per-edge radial MLP + tensor product, 0.342 MFLOP/edge for the 74->74 layer) / measured K3 time; the
+            # aggregate-then-transform rewrite executes far fewer FLOPs (reported separately, never claimed as achieved).
+            sec = tp["ms"] * 1e-3
+            gbs = tp["bytes"] / sec / 1e9
+            tf_ref = tp["flops_ref"] / sec / 1e12
+            peak_tf = peaks["bf16_tflops_sustained"]     # K3 is timed inside a long step: sustained figure
+            out["roofline"] = {"bound": "tensor", "achieved": tf_ref, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_ref / peak_tf,
+                               "traffic": K3_DRAM_BYTES_PER_CALL,
+                               "traffic_note": "ncu dram read+write bytes of one K3 call of the 74->74 conv layer (accumulate + transform), "
+                                               "profiles/r1; dominated by the accumulator workspace written once and read once",
+                               "kernel": "K3 = tp_accumulate_tc_kernel (tcgen05 3xTF32) + tp_transform_kernel, all launches of the timed region",
+                               "peak_source": peaks["source"] + ", dense bf16 sustained; 3xTF32 emulation can reach at most 1/6 of it",
+                               "launches": tp["launches"], "avg_launch_ms": tp["ms"] / tp["launches"],
+                               "share_of_step": tp["ms"] / (ms_step * opts.steps),
+                               "algorithmic_flops_per_launch": tp["flops_ref"] / tp["launches"],
                                "algorithmic_bytes_per_launch": tp["bytes"] / tp["launches"],
-                               "tflops_reference_formulation": tp["flops_ref"] / (tp["ms"] * 1e-3) / 1e12,
-                               "tflops_executed_fp32": tp["flops_exec"] / (tp["ms"] * 1e-3) / 1e12}
+                               "hbm_achieved_gbs": gbs, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_frac": gbs / peaks["hbm_gbs"],
+                               "tflops_executed": tp["flops_exec"] / sec / 1e12}
         if not opts.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(opts)
         print(json.dumps(out))

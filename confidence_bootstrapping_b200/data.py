@@ -121,7 +121,10 @@ class HeteroData:
         return self
 
     def to(self, device, non_blocking=False):
-        return self._apply(lambda t: t.to(device, non_blocking=non_blocking))
+        def mv(t):
+            _count_h2d(t, device)
+            return t.to(device, non_blocking=non_blocking)
+        return self._apply(mv)
 
     def cpu(self):
         return self.to("cpu")
@@ -134,9 +137,43 @@ def _is_cat_tensor(v):
     return torch.is_tensor(v) and v.dim() >= 1
 
 
+H2D_BYTES = 0   # bytes moved host -> device by the collate-to-device path and HeteroData.to (bench.py reads it)
+
+
+def _count_h2d(t, device):
+    global H2D_BYTES
+    if torch.is_tensor(t) and t.device.type == "cpu" and torch.device(device).type == "cuda":
+        H2D_BYTES += t.numel() * t.element_size()
+
+
+def _replicated(vals):
+    """True when every tensor of the list has the same content (the N copies of one complex that
+    inference.py / finetune_train.py make with copy.deepcopy share everything but the ligand pose)."""
+    v0 = vals[0]
+    if len(vals) < 2 or v0.device.type != "cpu" or v0.numel() < 1024:
+        return False
+    return all(v.shape == v0.shape and v.dtype == v0.dtype and (v.data_ptr() == v0.data_ptr() or torch.equal(v, v0)) for v in vals[1:])
+
+
+def _cat0(vals, device):
+    """torch.cat(vals, 0), landing on `device` when given.  Replicated host tensors cross the bus once and are
+    tiled on the device."""
+    if device is None:
+        return torch.cat(vals, 0)
+    if _replicated(vals):
+        _count_h2d(vals[0], device)
+        d = vals[0].to(device, non_blocking=True)
+        return d.repeat((len(vals),) + (1,) * (d.dim() - 1))
+    out = torch.cat(vals, 0)
+    _count_h2d(out, device)
+    return out.to(device, non_blocking=True)
+
+
 class Batch(HeteroData):
     @classmethod
-    def from_data_list(cls, data_list: List[HeteroData]):
+    def from_data_list(cls, data_list: List[HeteroData], device=None):
+        """Collate; with `device` the batch is assembled directly on that device (one transfer per attribute,
+        replicated attributes transferred once)."""
         b = cls()
         n = len(data_list)
         first = data_list[0]
@@ -151,7 +188,7 @@ class Batch(HeteroData):
             for k in first[nt].keys():
                 vals = [d[nt]._d[k] for d in data_list]
                 if _is_cat_tensor(vals[0]):
-                    st._d[k] = torch.cat(vals, 0)
+                    st._d[k] = _cat0(vals, device)
                     slices[nt][k] = [0] + list(np.cumsum([v.shape[0] for v in vals]))
                 else:
                     st._d[k] = vals
@@ -165,12 +202,20 @@ class Batch(HeteroData):
             for k in first[et].keys():
                 vals = [d[et]._d[k] for d in data_list]
                 if k == "edge_index":
-                    sh = [torch.tensor([[offs[et[0]][i]], [offs[et[2]][i]]], dtype=v.dtype, device=v.device)
-                          for i, v in enumerate(vals)]
-                    st._d[k] = torch.cat([v + s for v, s in zip(vals, sh)], 1)
+                    if device is not None and _replicated(vals):
+                        _count_h2d(vals[0], device)
+                        shifts = torch.tensor(np.stack([offs[et[0]][:n], offs[et[2]][:n]], 1), dtype=vals[0].dtype).to(device)
+                        st._d[k] = (vals[0].to(device).unsqueeze(0) + shifts.unsqueeze(2)).permute(1, 0, 2).reshape(2, -1)
+                    else:
+                        sh = [torch.tensor([[offs[et[0]][i]], [offs[et[2]][i]]], dtype=v.dtype, device=v.device)
+                              for i, v in enumerate(vals)]
+                        st._d[k] = torch.cat([v + s for v, s in zip(vals, sh)], 1)
+                        if device is not None:
+                            _count_h2d(st._d[k], device)
+                            st._d[k] = st._d[k].to(device)
                     slices[et][k] = [0] + list(np.cumsum([v.shape[1] for v in vals]))
                 elif _is_cat_tensor(vals[0]):
-                    st._d[k] = torch.cat(vals, 0)
+                    st._d[k] = _cat0(vals, device)
                     slices[et][k] = [0] + list(np.cumsum([v.shape[0] for v in vals]))
                 else:
                     st._d[k] = vals
@@ -179,9 +224,12 @@ class Batch(HeteroData):
                 continue
             vals = [d._g[k] for d in data_list]
             if _is_cat_tensor(vals[0]):
-                b._g[k] = torch.cat(vals, 0)
+                b._g[k] = _cat0(vals, device)
             elif torch.is_tensor(vals[0]):
                 b._g[k] = torch.stack(vals, 0)
+                if device is not None:
+                    _count_h2d(b._g[k], device)
+                    b._g[k] = b._g[k].to(device)
             else:
                 b._g[k] = vals
         b._g["_num_graphs"] = n
@@ -222,16 +270,17 @@ class Batch(HeteroData):
 class DataLoader:
     """Sequential, non-shuffling stand-in for torch_geometric.loader.DataLoader (sampling.py:78)."""
 
-    def __init__(self, dataset, batch_size=1, shuffle=False, **kw):
+    def __init__(self, dataset, batch_size=1, shuffle=False, device=None, **kw):
         assert not shuffle
-        self.dataset, self.batch_size = dataset, batch_size
+        self.dataset, self.batch_size, self.device = dataset, batch_size, device
 
     def __len__(self):
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
         for i in range(0, len(self.dataset), self.batch_size):
-            yield Batch.from_data_list([self.dataset[j] for j in range(i, min(i + self.batch_size, len(self.dataset)))])
+            yield Batch.from_data_list([self.dataset[j] for j in range(i, min(i + self.batch_size, len(self.dataset)))],
+                                       device=self.device)
 
 
 def subgraph(subset, edge_index, edge_attr=None, relabel_nodes=False, num_nodes=None):

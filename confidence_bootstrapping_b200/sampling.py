@@ -161,11 +161,12 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     assert not (return_full_trajectory or return_features or pivot), "Not implemented yet in new inference version"
     assert not asyncronous_noise_schedule
 
-    loader = DataLoader(data_list, batch_size=batch_size)
+    # batches are collated straight onto the device: attributes shared by the N copies of a complex cross the bus once
+    loader = DataLoader(data_list, batch_size=batch_size, device=device)
     mask_rotate = _mask_rotate_of(data_list[0])
     confidence = None
     if confidence_model is not None:
-        filtering_loader = iter(DataLoader(filtering_data_list, batch_size=batch_size)) if filtering_data_list is not None else None
+        filtering_loader = iter(DataLoader(filtering_data_list, batch_size=batch_size, device=device)) if filtering_data_list is not None else None
         confidence = []
     if not _is_iterable(temp_sampling):
         temp_sampling = [temp_sampling] * 3

@@ -63,16 +63,24 @@ class EquivariantBatchNorm(nn.Module):
         for m, l, p in self.irreps:
             dims += [2 * l + 1] * m
             is_s += [l == 0 and p == 1] * m
-        self.register_buffer("_dims", torch.tensor(dims, dtype=torch.long), persistent=False)
-        self.register_buffer("_is_scalar", torch.tensor(is_s, dtype=torch.bool), persistent=False)
+        # static index tables (no boolean masks / repeat_interleave at run time: those synchronise the host)
+        self.register_buffer("_scalar_idx", torch.tensor([i for i, f in enumerate(is_s) if f], dtype=torch.long), persistent=False)
+        self.register_buffer("_feat_of_chan", torch.tensor([i for i, d in enumerate(dims) for _ in range(d)], dtype=torch.long),
+                             persistent=False)
+        self._affine_cache = None
 
     def affine(self):
-        """(scale[d], shift[d]) such that eval-mode BN(x) = x * scale + shift, per feature channel."""
-        scale_c = self.weight * torch.rsqrt(self.running_var + self.eps)
-        shift_c = torch.zeros_like(scale_c)
-        shift_c[self._is_scalar] = self.bias - self.running_mean * scale_c[self._is_scalar]
-        return (torch.repeat_interleave(scale_c, self._dims).contiguous(),
-                torch.repeat_interleave(shift_c, self._dims).contiguous())
+        """(scale[d], shift[d]) such that eval-mode BN(x) = x * scale + shift, per feature channel.
+        Cached until a parameter or running statistic changes."""
+        key = tuple((t.data_ptr(), t._version) for t in (self.weight, self.bias, self.running_mean, self.running_var))
+        if self._affine_cache is None or self._affine_cache[0] != key:
+            with torch.no_grad():
+                scale_c = self.weight * torch.rsqrt(self.running_var + self.eps)
+                shift_c = torch.zeros_like(scale_c)
+                shift_c.index_copy_(0, self._scalar_idx, self.bias - self.running_mean * scale_c.index_select(0, self._scalar_idx))
+                self._affine_cache = (key, scale_c.index_select(0, self._feat_of_chan).contiguous(),
+                                      shift_c.index_select(0, self._feat_of_chan).contiguous())
+        return self._affine_cache[1], self._affine_cache[2]
 
 
 @dataclass

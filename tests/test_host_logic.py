@@ -125,3 +125,21 @@ def test_rotatable_masks_orientation():
     for k, (u, v) in enumerate(ei[me]):
         assert not mr[k, u] and mr[k, v]          # utils/torsion.py:81-82
         assert 1 < mr[k].sum() <= g["ligand"].num_nodes // 2 + 1
+
+
+def test_collate_to_device_matches_host_collate():
+    """Batch.from_data_list(device=...) (replicated attributes transferred once and tiled) == plain collate."""
+    import copy
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    g = make_complex(3, 40, 12, all_atoms=True, lm_dim=64)
+    dl = [copy.deepcopy(g) for _ in range(3)]
+    for i, d in enumerate(dl):
+        d["ligand"].pos = d["ligand"].pos + float(i)          # the one attribute that differs between the copies
+    a, b = Batch.from_data_list(dl), Batch.from_data_list(dl, device="cpu")
+    for key, st in a._stores.items():
+        for k, v in st.items():
+            w = b[key]._d[k]
+            if torch.is_tensor(v):
+                assert v.dtype == w.dtype and torch.equal(v, w), (key, k)
+    assert a.num_graphs == b.num_graphs == 3
