@@ -429,6 +429,7 @@ __device__ __forceinline__ void cp_async_bytes16(void* smem_dst, const void* gsr
 }
 
 constexpr int MAXT = 4;   // terms of a thread's f-row kept in registers
+constexpr int ITEM_BLOCK = 1;   // consecutive (node, slot) items dealt to a persistent CTA at a time
 
 struct FRowCtx {
     const float* xs; const float* shs; const cb_tp_term* terms_s; unsigned char* Fhi; unsigned char* Flo;
@@ -567,11 +568,14 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         e0 = __ldg(sg.rowptr + (node - sg.n0));
         e1 = __ldg(sg.rowptr + (node - sg.n0) + 1);
     };
+    // items are dealt to the persistent CTAs in blocks of ITEM_BLOCK consecutive (node, slot) pairs: neighbouring nodes
+    // share their graph (cached per-graph bias), their rowptr / projection cache lines and their workspace tile
+    auto next_item = [&](int item) { return (item % ITEM_BLOCK) < ITEM_BLOCK - 1 ? item + 1 : item + 1 + (int)(gridDim.x - 1) * ITEM_BLOCK; };
     auto open_item = [&](Chunk& c, int item, int q) {
         // first non-empty segment of the first non-empty item at or after `item`
         c.valid = false;
 #pragma unroll 1
-        for (; item < n_items; item += gridDim.x) {
+        for (; item < n_items; item = next_item(item)) {
             while (q + 1 < st.n_slots && item >= st.item_off[q + 1]) ++q;
             const int node = st.lo[q] + (item - st.item_off[q]);
 #pragma unroll 1
@@ -615,7 +619,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 return n;
             }
         }
-        e1 = open_item(n, c.item + gridDim.x, c.q);
+        e1 = open_item(n, next_item(c.item), c.q);
         return n;
     };
     auto load_cols = [&](const Chunk& c, int b) {
@@ -646,8 +650,23 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     };
 
     Chunk cur;
-    int cur_e1 = open_item(cur, blockIdx.x, 0);
+    int cur_e1 = open_item(cur, blockIdx.x * ITEM_BLOCK, 0);
     int buf = 0;
+    // per-item constants of the hidden layer, prefetched one chunk ahead / cached in registers (threads tid < H):
+    //   hbase[q] = b1[q] + W1e[q] . e_post[graph]   (changes with the slot or the graph)   +  P_agg[node][q]
+    auto load_pagg = [&](const Chunk& c) {
+        const cb_tp_segment& s0 = a.segs[st.first_seg[c.q]];
+        return (tid < H && s0.P_agg) ? __ldg(s0.P_agg + (size_t)c.node * s0.ldp_agg + tid) : 0.0f;
+    };
+    auto load_graph = [&](const Chunk& c) { return a.agg_graph ? __ldg(a.agg_graph + c.node) : 0; };
+    float pagg_cur = 0.0f, pagg_nxt = 0.0f, hb_const = 0.0f;
+    int graph_cur = 0, graph_nxt = 0, hb_q = -1, hb_graph = -1;
+    if (cur.valid) {
+        pagg_cur = load_pagg(cur);
+        graph_cur = load_graph(cur);
+    }
+    size_t ws_off = 0;
+    int ws_stride = 0;
     if (cur.valid) {
         load_cols(cur, 0);
         __syncthreads();
@@ -661,6 +680,10 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         int nxt_e1 = cur_e1;
         Chunk nxt = advance(cur, nxt_e1);
         if (nxt.valid) load_cols(nxt, buf ^ 1);
+        if (nxt.valid && nxt.first) {       // the next item's per-node constants arrive while this chunk is processed
+            pagg_nxt = load_pagg(nxt);
+            graph_nxt = load_graph(nxt);
+        }
         if (cur.first) {
             // ---- per-item setup: edge-embedding slice of the first Linear (on slot change), constant part of h
             const cb_tp_segment& s0 = a.segs[st.first_seg[cur.q]];
@@ -680,18 +703,22 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 }
                 staged_slot = cur.q;
             }
-            const int graph = a.agg_graph ? a.agg_graph[cur.node] : 0;
-#pragma unroll 1
-            for (int qq = tid; qq < H; qq += THREADS) {
-                float v = s0.b1[qq];
-                if (s0.P_agg) v += s0.P_agg[(size_t)cur.node * s0.ldp_agg + qq];
-                if (s0.e_post) {
-                    const float* ep = s0.e_post + (size_t)graph * ne;
+            if (tid < H) {
+                if (hb_q != cur.q || (s0.e_post && hb_graph != graph_cur)) {
+                    float v = __ldg(s0.b1 + tid);
+                    if (s0.e_post) {
+                        const float* ep = s0.e_post + (size_t)graph_cur * ne;
 #pragma unroll 4
-                    for (int c = 0; c < ne; ++c) v = fmaf(__ldg(s0.W1e + (size_t)qq * s0.ldw1 + c), ep[c], v);
+                        for (int c = 0; c < ne; ++c) v = fmaf(__ldg(s0.W1e + (size_t)tid * s0.ldw1 + c), __ldg(ep + c), v);
+                    }
+                    hb_const = v;
+                    hb_q = cur.q;
+                    hb_graph = graph_cur;
                 }
-                hbase[qq] = v;
+                hbase[tid] = hb_const + pagg_cur;
             }
+            // where the finished tile goes (rowptr lookups of the node's workspace tile): needed only by the epilogue
+            ws_off = ws_place(a, st, cur.q, cur.node, n_rows, HA, lane, ws_stride);
         }
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();                                   // gather(cur), cols(nxt), hbase visible to everyone
@@ -851,8 +878,8 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 ++waited;
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            int row_stride;
-            float* Aout = a.workspace + ws_place(a, st, cur.q, cur.node, n_rows, HA, lane, row_stride);
+            const int row_stride = ws_stride;
+            float* Aout = a.workspace + ws_off;
             const int lg = warp & 3;                 // TMEM lane group this warp may access
             constexpr int STG_LD = 36;               // floats per staged row: 144-byte stride keeps float4 accesses conflict-free
             float* stg = reinterpret_cast<float*>(smraw + L.fhi) + warp * 32 * STG_LD;
@@ -895,6 +922,10 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();   // TMEM tile fully read before the next item's first MMA overwrites it
+        }
+        if (nxt.valid && nxt.first) {
+            pagg_cur = pagg_nxt;
+            graph_cur = graph_nxt;
         }
         cur = nxt;
         cur_e1 = nxt_e1;
@@ -1276,7 +1307,8 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
                 return CB_ERR_CUDA;
             }
             const int per_sm = smem <= 112 * 1024 ? 2 : 1;
-            const int grid = items < CB_NUM_SMS * per_sm ? (int)items : CB_NUM_SMS * per_sm;
+            const int blocks = (int)((items + tc::ITEM_BLOCK - 1) / tc::ITEM_BLOCK);
+            const int grid = blocks < CB_NUM_SMS * per_sm ? blocks : CB_NUM_SMS * per_sm;
             tc::tp_accumulate_tc_kernel<<<grid, tc::THREADS, smem, st>>>(*a, (int)items);
             CB_CHECK_LAUNCH("cb_tp_conv_forward(accumulate, tcgen05)");
             rc = CB_OK;
