@@ -182,7 +182,14 @@ class TpTimer:
                 counters[c.data_ptr()] = c
         for (s, e, meta, d_in, d_out, ne, S, H) in self.records:
             layer = meta["layer"]
-            E = [int(c.item()) for c in meta["edge_counters"]]
+            E = []
+            for c, (edges, gate) in zip(meta["edge_counters"], meta["edge_gates"]):
+                if gate is None:
+                    E.append(int(c.item()))
+                else:   # dead-output pruning: only the edges of gated-in aggregation nodes are processed (and counted)
+                    deg = (edges.rowptr[1:edges.n_agg + 1] - edges.rowptr[:edges.n_agg]).long()
+                    keep = gate.rowptr[1:gate.n_agg + 1] > gate.rowptr[:gate.n_agg]
+                    E.append(int((deg * keep).sum().item()))
             numel, K1 = layer.weight_numel, layer.n_edge_features
             params = len(meta["groups"]) * (H * K1 + H + numel * H + numel)
             R = layer.program.n_rows

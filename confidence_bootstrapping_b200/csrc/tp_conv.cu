@@ -65,6 +65,19 @@ __host__ __device__ inline void build_slots(const cb_tp_conv_args& a, SlotTable&
     }
 }
 
+// edge range of `node` in segment sg; empty when the segment's gate says the node's output is never read
+__device__ __forceinline__ void seg_edges(const cb_tp_segment& sg, int node, int& e0, int& e1) {
+    const int i = node - sg.n0;
+    e0 = __ldg(sg.rowptr + i);
+    e1 = __ldg(sg.rowptr + i + 1);
+    if (sg.gate_rowptr != nullptr && __ldg(sg.gate_rowptr + i + 1) <= __ldg(sg.gate_rowptr + i)) e1 = e0;
+}
+__device__ __forceinline__ int seg_degree(const cb_tp_segment& sg, int node) {
+    int e0, e1;
+    seg_edges(sg, node, e0, e1);
+    return e1 - e0;
+}
+
 // Where the accumulator of (slot q, node) lives: called by all 32 lanes of a warp (lane = node of the tile).
 // Returns the float offset of element (row 0, column 0) and the row stride in floats.
 __device__ __forceinline__ size_t ws_place(const cb_tp_conv_args& a, const SlotTable& st, int q, int node, int n_rows, int HA, int lane,
@@ -76,7 +89,7 @@ __device__ __forceinline__ size_t ws_place(const cb_tp_conv_args& a, const SlotT
 #pragma unroll 1
         for (int s = st.first_seg[q]; s < st.first_seg[q] + st.n_segs[q]; ++s) {
             const cb_tp_segment& sg = a.segs[s];
-            deg += __ldg(sg.rowptr + (other - sg.n0) + 1) - __ldg(sg.rowptr + (other - sg.n0));
+            deg += seg_degree(sg, other);
         }
     }
     const unsigned act = __ballot_sync(0xffffffffu, deg > 0);
@@ -184,7 +197,7 @@ tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
         int deg = 0;
         for (int s = seg0; s < seg0 + nseg; ++s) {
             const cb_tp_segment& sg = a.segs[s];
-            deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
+            deg += seg_degree(sg, node);
         }
         if (deg == 0) continue;  // block-uniform; the transform kernel skips (node, slot) pairs without edges
 
@@ -225,7 +238,8 @@ tp_accumulate_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
 
         for (int s = seg0; s < seg0 + nseg; ++s) {
             const cb_tp_segment& sg = a.segs[s];
-            const int e0 = sg.rowptr[node - sg.n0], e1 = sg.rowptr[node - sg.n0 + 1];
+            int e0, e1;
+            seg_edges(sg, node, e0, e1);
             for (int base = e0; base < e1; base += CH) {
                 const int n = min(CH, e1 - base);
                 // ---- gather raw operands of the chunk
@@ -565,8 +579,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     // ---- chunk iterator (block-uniform): items of this CTA in increasing order, their segments, KC edges at a time
     auto seg_range = [&](int seg, int node, int& e0, int& e1) {
         const cb_tp_segment& sg = a.segs[seg];
-        e0 = __ldg(sg.rowptr + (node - sg.n0));
-        e1 = __ldg(sg.rowptr + (node - sg.n0) + 1);
+        seg_edges(sg, node, e0, e1);
     };
     // items are dealt to the persistent CTAs in blocks of ITEM_BLOCK consecutive (node, slot) pairs: neighbouring nodes
     // share their graph (cached per-graph bias), their rowptr / projection cache lines and their workspace tile
@@ -1111,7 +1124,7 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
 #pragma unroll 1
                 for (int s = st.first_seg[q]; s < st.first_seg[q] + st.n_segs[q]; ++s) {
                     const cb_tp_segment& sg = a.segs[s];
-                    deg += sg.rowptr[node - sg.n0 + 1] - sg.rowptr[node - sg.n0];
+                    deg += seg_degree(sg, node);
                 }
             }
             if (deg > 0) it = 0;

@@ -343,9 +343,12 @@ class TensorProductScoreModel(nn.Module):
         n_layers = len(self.conv_layers)
         for l, layer in enumerate(self.conv_layers):
             if l < n_layers - 1:
+                # the last layer reads receptor rows only through rec->lig cross edges, so in the layer before it only
+                # receptors with a cross edge (= a non-empty row of the flipped list `rl`) need their rec->rec update
+                gate = rl if l == n_layers - 2 else None
                 segs = lig_segments(g[0], NL) + [
                     Segment(lr, lr_attr, lr_sh, g[1], 0, NL, col_off=NL),
-                    Segment(st.rec_edges, st.rec_e_attr, st.rec_sh, g[2], NL, NL + NR, col_off=NL, e_post=rec_sigma_emb),
+                    Segment(st.rec_edges, st.rec_e_attr, st.rec_sh, g[2], NL, NL + NR, col_off=NL, e_post=rec_sigma_emb, gate=gate),
                     Segment(rl, rl_attr, rl_sh, g[3], NL, NL + NR, col_off=0)]
                 x = layer.run(x, segs, NL + NR, ns, agg_graph=node_graph, residual=x, **cols)
             else:

@@ -94,6 +94,7 @@ class Segment:
     n1: int = 0
     col_off: int = 0                     # offset of the neighbour node type inside x
     e_post: Optional[torch.Tensor] = None  # [B, ne]
+    gate: Optional["EdgeList"] = None      # aggregation nodes without an edge in `gate` are skipped (dead-output pruning)
     slot: Optional[int] = None           # segments sharing a slot share (n0, n1, group) and one accumulator
 
 
@@ -225,6 +226,9 @@ class TensorProductConvLayer(nn.Module):
             sg.e_attr, sg.sh = _lib.f32(s.e_attr, "e_attr"), _lib.f32(s.sh, "sh")
             assert s.e_attr.shape[1] == e_cols[1] and s.sh.shape[1] == P.sh_dim
             sg.e_post = _lib.f32(s.e_post, "e_post", allow_none=True)
+            if s.gate is not None:
+                assert s.gate.n_agg == s.n1 - s.n0, "gate edge list must cover the segment's aggregation nodes"
+                sg.gate_rowptr = _lib.i32(s.gate.rowptr, "gate.rowptr")
             if s.group in P_agg:
                 t, off = P_agg[s.group]
                 sg.P_agg, sg.ldp_agg = t.data_ptr() + 4 * off, t.shape[1]
@@ -243,7 +247,8 @@ class TensorProductConvLayer(nn.Module):
         a.out = out.data_ptr()
         # bookkeeping for profilers (bench.py): which edge counters / sizes this launch covers
         a._meta = dict(layer=self, n_in=int(x.shape[0]), n_out=int(n_out), groups=groups,
-                       edge_counters=[s.edges.n_edges_dev for s in segments])
+                       edge_counters=[s.edges.n_edges_dev for s in segments],
+                       edge_gates=[(s.edges, s.gate) for s in segments])
         # workspace: one R x (H+4) accumulator per (node, slot); process the nodes in chunks if it would be huge
         per_item = P.n_rows * (H + 4)
         a.node_begin, a.node_end = 0, n_out

@@ -147,6 +147,9 @@ typedef struct {
     int32_t col_off;        /* added to col[e] to index x / P_nbr (node tables are concatenated)  */
     int32_t slot;           /* segments with the same slot share (n0,n1), the radial MLP and one accumulator;
                                slots are numbered 0.. in segment order, equal slots adjacent        */
+    const int32_t* gate_rowptr; /* optional [n1-n0+1] CSR row pointer of ANOTHER edge list over the same node range: nodes
+                               with no edge there are skipped (treated as degree 0) -- dead-output pruning, e.g. receptor
+                               rows of the last full conv layer that no rec->lig edge reads (score_model.py:372-374) */
 } cb_tp_segment;
 #define CB_MAX_SEGS 12
 typedef struct {

@@ -253,3 +253,42 @@ def test_tp_conv_layer_ffma_accumulate(in_ir, sh_l, out_ir, faster, groups, nef)
         finally:
             tensor_layers.ACCUM_MODE = old
     assert rel_err(got, want) < 1e-5
+
+
+@pytest.mark.gpu
+def test_tp_conv_gate_prunes_dead_outputs():
+    """Segment.gate (cb_tp_segment.gate_rowptr): aggregation nodes without an edge in the gate list are skipped
+    (output = epilogue of an empty sum); every other node is bit-identical to the ungated call."""
+    from confidence_bootstrapping_b200.graph import static_edges
+    from confidence_bootstrapping_b200.tensor_layers import Segment, TensorProductConvLayer
+    from helpers import randomize_norm_stats
+    torch.manual_seed(0)
+    layer = TensorProductConvLayer(SEQ[3], "1x0e + 1x1o", SEQ[3], 32, residual=True, batch_norm=True, hidden_features=96,
+                                   faster=True, edge_groups=2)
+    randomize_norm_stats(layer, seed=1)
+    layer = layer.eval().cuda()
+    n, e = 100, 1500
+    x = torch.randn(n, 74, device="cuda")
+    ei_a, ei_b = _random_graph(3, n, e).cuda(), _random_graph(4, n, e // 2).cuda()
+    gate_ei = torch.stack([torch.arange(0, n, 3), torch.zeros(len(range(0, n, 3)), dtype=torch.long)]).cuda()   # every 3rd node
+    ea, eb = torch.randn(e, 32, device="cuda"), torch.randn(e // 2, 32, device="cuda")
+    sha = o3.spherical_harmonics([0, 1], torch.randn(e, 3), True, "component").cuda()
+    shb = o3.spherical_harmonics([0, 1], torch.randn(e // 2, 3), True, "component").cuda()
+    (la, pa), (lb, pb), (lg, _) = static_edges(ei_a, n), static_edges(ei_b, n), static_edges(gate_ei, n)
+
+    def run(gate):
+        segs = [Segment(la, ea[pa].contiguous(), sha[pa].contiguous(), 0, 0, n, gate=gate),
+                Segment(lb, eb[pb].contiguous(), shb[pb].contiguous(), 1, 0, n)]
+        with torch.no_grad():
+            return layer.run(x, segs, n, 0, (0, 32), residual=x)
+
+    full, gated = run(None), run(lg)
+    only_b = None
+    with torch.no_grad():
+        only_b = layer.run(x, [Segment(lb, eb[pb].contiguous(), shb[pb].contiguous(), 1, 0, n)], n, 0, (0, 32), residual=x)
+    keep = torch.zeros(n, dtype=torch.bool, device="cuda")
+    keep[::3] = True
+    assert torch.equal(gated[keep], full[keep])
+    # gated-out nodes only see group-1 edges; their mean is over those edges alone
+    assert rel_err(gated[~keep], only_b[~keep]) < 1e-5
+    assert not torch.equal(gated[~keep], full[~keep])
