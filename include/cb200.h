@@ -108,9 +108,11 @@ int cb_edge_featurize(const cb_edge_feat_args* a, void* stream);
  * edge segment s,   sum_e tp_e = T_s( sum_e f_e (x) [h_e ; 1] ),   f_e = CG products of x[col[e]]
  * and sh_e (the "program"), h_e = relu(b1 + P_agg[i] + P_nbr[col[e]] + W1e (e_attr[e] + e_post[g(i)])),
  * T_s = contraction with (W2, b2).  The [E, weight_numel] tensor is never materialised.
- * Two launches: (a) accumulate, one CTA per (node, slot), A = sum_e f_e (x) [h_e;1] in registers, written
- * once to the workspace; (b) transform + epilogue, one CTA per 32 nodes, which streams every W2 row once
- * per 32 nodes and finishes with mean / BatchNorm / residual.
+ * Two launches: (a) accumulate -- persistent CTAs walk the (node, slot) pairs; per chunk of 16 edges the hidden
+ * layer and the rank-16 update A += F^T [h;1] run as tcgen05 3xTF32 MMAs with TMEM accumulators (accum_mode 2;
+ * accum_mode 1 keeps A in fp32 FFMA register tiles), the finished tile is written once to the workspace;
+ * (b) transform + epilogue -- one CTA per 32 nodes streams the tile's accumulator rows and the W2a rows with
+ * bulk copies through a shared-memory ring and finishes with mean / BatchNorm / residual.
  */
 typedef struct {            /* one CG product term of an f-row: coef * x[x_idx] * sh[sh_idx] */
     int16_t x_idx; int16_t sh_idx; float coef;
