@@ -48,16 +48,39 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self._stop = index, [], threading.Event()
 
+    def _nvml(self):
+        """In-process NVML handle (a forked nvidia-smi every 200 ms perturbs the launching thread)."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            return pynvml, h
+        except Exception:
+            return None, None
+
     def _run(self):
+        nv, h = self._nvml()
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if nv is not None:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                    get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                    bits = int(get(h))
+                    flag = lambda b: "Active" if bits & b else "Not Active"   # noqa: E731
+                    self.rows.append([str(sm), str(mx), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.1 if nv is not None else 0.5)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -172,24 +195,25 @@ class TpTimer:
         s.record()
         yield
         e.record()
-        self.records.append((s, e, a._meta, a.d_in, a.d_out, a.ne, a.S, a.H))
+        meta = a._meta
+        # keep only 1-element device counters (cloned: the edge lists themselves must stay free for the allocator)
+        parts = []
+        for c, (edges, gate) in zip(meta["edge_counters"], meta["edge_gates"]):
+            if gate is None:
+                parts.append(c.reshape(1))
+            else:   # dead-output pruning: only the edges of gated-in aggregation nodes are processed (and counted)
+                deg = edges.rowptr[1:edges.n_agg + 1] - edges.rowptr[:edges.n_agg]
+                keep = gate.rowptr[1:gate.n_agg + 1] > gate.rowptr[:gate.n_agg]
+                parts.append((deg * keep).sum().reshape(1).to(c.dtype))
+        counts = torch.cat(parts)        # one tiny launch per K3 call
+        self.records.append((s, e, dict(layer=meta["layer"], n_in=meta["n_in"], n_out=meta["n_out"], groups=meta["groups"], counts=counts),
+                             a.d_in, a.d_out, a.ne, a.S, a.H))
 
     def summarise(self):
         tot_ms, tot_bytes, tot_flops_ref, tot_flops_exec, n = 0.0, 0.0, 0.0, 0.0, 0
-        counters = {}
-        for (_, _, meta, *_r) in self.records:
-            for c in meta["edge_counters"]:
-                counters[c.data_ptr()] = c
         for (s, e, meta, d_in, d_out, ne, S, H) in self.records:
             layer = meta["layer"]
-            E = []
-            for c, (edges, gate) in zip(meta["edge_counters"], meta["edge_gates"]):
-                if gate is None:
-                    E.append(int(c.item()))
-                else:   # dead-output pruning: only the edges of gated-in aggregation nodes are processed (and counted)
-                    deg = (edges.rowptr[1:edges.n_agg + 1] - edges.rowptr[:edges.n_agg]).long()
-                    keep = gate.rowptr[1:gate.n_agg + 1] > gate.rowptr[:gate.n_agg]
-                    E.append(int((deg * keep).sum().item()))
+            E = [int(v) for v in meta["counts"].tolist()]
             numel, K1 = layer.weight_numel, layer.n_edge_features
             params = len(meta["groups"]) * (H * K1 + H + numel * H + numel)
             R = layer.program.n_rows

@@ -11,7 +11,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcb200.so")
 SOURCES = ["cabi.cu", "radius.cu", "edge_feat.cu", "tp_conv.cu", "sde_step.cu", "crop.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("CB200_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

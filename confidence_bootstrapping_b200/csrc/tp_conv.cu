@@ -489,6 +489,13 @@ __device__ __forceinline__ void f_row(const FRowCtx& c, const int (&t_xi)[MAXT],
     }
 }
 
+#ifdef CB_PHASE_TIMING
+__device__ unsigned long long cb_dbg_phase[2][12];
+#define PH_MARK(k) do { if (ph_on) { const long long t_ = clock64(); ph[k] += t_ - ph_t; ph_t = t_; } } while (0)
+#else
+#define PH_MARK(k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(THREADS, 2)
 tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -685,8 +692,13 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         __syncthreads();
         issue_gather(cur, 0);
     }
+#ifdef CB_PHASE_TIMING
+    const bool ph_on = (tid == 0 || tid == 224);
+    long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ph_t = clock64();
+#endif
 #pragma unroll 1
     while (cur.valid) {
+        PH_MARK(9);
         const cb_tp_segment& sg = a.segs[cur.seg];
         const int n = cur.n;
         cur.last = !has_more(cur, cur_e1);
@@ -733,14 +745,14 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             // where the finished tile goes (rowptr lookups of the node's workspace tile): needed only by the epilogue
             ws_off = ws_place(a, st, cur.q, cur.node, n_rows, HA, lane, ws_stride);
         }
+        PH_MARK(0);
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        PH_MARK(10);
         __syncthreads();                                   // gather(cur), cols(nxt), hbase visible to everyone
+        PH_MARK(1);
         if (nxt.valid) issue_gather(nxt, buf ^ 1);         // overlaps everything below
 
-        if (waited < commits) {                            // operand tiles are free once the previous MMAs completed
-            mbar_wait(&mma_bar, waited & 1);
-            ++waited;
-        }
+        PH_MARK(2);
         const float* xs = xs_of(buf);
         const float* shs = shs_of(buf);
         const float* es = es_of(buf);
@@ -775,6 +787,13 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 dwh += (2 * LBO) >> 4; dwl += (2 * LBO) >> 4; deh += (2 * LBO) >> 4; del += (2 * LBO) >> 4;
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&h_bar)) : "memory");
+        }
+        PH_MARK(3);
+        // the F / H~ operand tiles are free once the previous chunk's MMAs completed; their latency has been overlapped with
+        // the iterator, the gather issue and the hidden-layer MMA above (which only touch the E / W1e tiles and D_h)
+        if (waited < commits) {
+            mbar_wait(&mma_bar, waited & 1);
+            ++waited;
         }
         // ---- F^T tile: row r = f-row, column = edge; hi/lo TF32 split.  Loops stay rolled on purpose:
         // the kernel must fit the 32 KB instruction cache (an unrolled build stalled on instruction fetch).
@@ -819,8 +838,10 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         // ---- H~ tile: row q = hidden unit (row H = constant 1), column = edge.  The pre-activations come back from
         // TMEM one hidden unit per lane (warps 0-3: edges 0-7, warps 4-7: edges 8-15) -- exactly one row of the
         // K-major operand tile -- and get the node / neighbour projections, the ReLU and the hi/lo split.
+        PH_MARK(4);
         mbar_wait(&h_bar, h_phase);
         h_phase ^= 1u;
+        PH_MARK(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
             const int qq = (warp & 3) * 32 + lane, eh = warp >> 2;
@@ -861,7 +882,9 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+        PH_MARK(6);
         __syncthreads();
+        PH_MARK(11);
         // ---- one thread issues the MMAs of this chunk and commits them to the barrier
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -884,6 +907,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                          : "memory");
         }
         ++commits;
+        PH_MARK(7);
         if (cur.last) {
             // ---- epilogue: wait for the last MMAs, read the tile back from TMEM, write it to the workspace
             while (waited < commits) {
@@ -936,6 +960,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();   // TMEM tile fully read before the next item's first MMA overwrites it
         }
+        PH_MARK(8);
         if (nxt.valid && nxt.first) {
             pagg_cur = pagg_nxt;
             graph_cur = graph_nxt;
@@ -944,6 +969,10 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         cur_e1 = nxt_e1;
         buf ^= 1;
     }
+#ifdef CB_PHASE_TIMING
+    if (ph_on)
+        for (int k = 0; k < 12; ++k) atomicAdd(&cb_dbg_phase[tid == 0 ? 0 : 1][k], (unsigned long long)ph[k]);
+#endif
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) {
@@ -1260,6 +1289,18 @@ int launch_accumulate(const cb_tp_conv_args* a, int items, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef CB_PHASE_TIMING
+extern "C" int cb_debug_phases(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tc::cb_dbg_phase, sizeof(unsigned long long) * 24);
+    if (reset) {
+        unsigned long long z[24] = {0};
+        cudaMemcpyToSymbol(tc::cb_dbg_phase, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 extern "C" int64_t cb_tp_conv_items(const cb_tp_conv_args* a) {
     if (a == nullptr || a->n_segs < 0 || a->n_segs > CB_MAX_SEGS) return -1;

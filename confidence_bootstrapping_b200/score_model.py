@@ -61,6 +61,17 @@ class AtomEncoder(nn.Module):
         return emb
 
 
+def _segment_sum(x, st):
+    """Per-graph sum over the ligand rows as one small GEMM with the (cached) graph-membership matrix: fixed summation
+    order and no host synchronisation, so the whole CUDA path stays bit-reproducible (index_add_ / scatter use
+    floating-point atomics, torch.segment_reduce reads its offsets on the host)."""
+    m = getattr(st, "lig_membership", None)
+    if m is None:
+        m = (st.lig_batch.unsqueeze(0) == torch.arange(st.B, dtype=st.lig_batch.dtype, device=x.device).unsqueeze(1)).float()
+        st.lig_membership = m
+    return m @ x
+
+
 class GaussianSmearing(nn.Module):
     """exp(coeff * (d - offset_k)^2) (score_model.py:667-677); evaluated inside K2."""
 
@@ -365,7 +376,7 @@ class TensorProductScoreModel(nn.Module):
     def _score_heads(self, data, st, emb, lig_x, lig_pos, sigma_emb, tr_sigma, rot_sigma, tor_sigma):
         ns, lmax, dev, B = self.ns, self.sh_lmax, st.dev, st.B
         # ---- translation / rotation head (score_model.py:394-420)
-        center = torch.zeros((B, 3), device=dev).index_add_(0, st.lig_batch.long(), lig_pos) * st.inv_nl
+        center = _segment_sum(lig_pos, st) * st.inv_nl
         graph_ids = torch.arange(B, dtype=torch.int32, device=dev)
         c_attr, c_sh = emb.center(st.center_edges, center.contiguous(), lig_pos, graph_ids, sigma_emb, lmax)
         seg = [Segment(st.center_edges, c_attr, c_sh, 0, 0, B)]
@@ -426,6 +437,6 @@ class TensorProductScoreModel(nn.Module):
             scalar = scalar[:, self.atom_num_confidence_outputs:]
         else:
             atom_confidence = torch.zeros((len(lig_x),), device=lig_x.device)
-        pooled = torch.zeros((st.B, scalar.shape[1]), device=lig_x.device).index_add_(0, st.lig_batch.long(), scalar) * st.inv_nl
+        pooled = _segment_sum(scalar, st) * st.inv_nl
         confidence = self.confidence_predictor(pooled).squeeze(dim=-1)
         return confidence, atom_confidence

@@ -25,6 +25,7 @@ ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
 # accumulate kernel of K3: 2 = tcgen05 3xTF32 UMMA + TMEM accumulator (default);
 # 1 = fp32 FFMA register tiles (kept for shapes outside the UMMA tile limits and for A/B measurements)
 ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "2"))
+FOLD_E_POST = True            # fold W1e.e_post[graph] into the node projection on the host (tests switch it off to cover the kernel path)
 DEBUG_KEEP_WORKSPACE = None   # tests may set this to a list to inspect the K3 accumulators
 WORKSPACE_BYTES = 6 << 30  # cap on the K3 accumulator workspace; larger layers are processed in node chunks
 
@@ -200,6 +201,24 @@ class TensorProductConvLayer(nn.Module):
             pa = (src @ Wa.t()).contiguous()
             for k, g in enumerate(groups):
                 P_agg[g] = (pa, k * H)
+        # per-graph edge-embedding offsets (e_post) are constant per aggregation node: fold W1e.e_post[graph(node)] into the
+        # node projection instead of re-deriving it for every (node, slot) inside the kernel.  Only when every segment of
+        # the group agrees on (e_post, node range); otherwise the kernel's own e_post path handles it.
+        folded = set()
+        if FOLD_E_POST and agg_cols is not None and agg_graph is not None:
+            by_group = {}
+            for s in segments:
+                by_group.setdefault(s.group, set()).add((None if s.e_post is None else s.e_post.data_ptr(), s.n0, s.n1))
+            graph_l = None
+            for s in segments:
+                if s.e_post is None or s.group in folded or len(by_group[s.group]) != 1:
+                    continue
+                if graph_l is None:
+                    graph_l = agg_graph.long()
+                t, off = P_agg[s.group]
+                W1e = self._fc(s.group)[0].weight[:, e_cols[0]:e_cols[0] + e_cols[1]]
+                t[s.n0:s.n1, off:off + H] += (s.e_post @ W1e.t()).index_select(0, graph_l[s.n0:s.n1])
+                folded.add(s.group)
         out = torch.empty((n_out, P.d_out), dtype=torch.float32, device=dev)
         a = _lib.TpConvArgs()
         a.x = _lib.f32(x, "x")
@@ -225,7 +244,7 @@ class TensorProductConvLayer(nn.Module):
             sg.rowptr, sg.col = _lib.i32(s.edges.rowptr, "rowptr"), _lib.i32(s.edges.col, "col")
             sg.e_attr, sg.sh = _lib.f32(s.e_attr, "e_attr"), _lib.f32(s.sh, "sh")
             assert s.e_attr.shape[1] == e_cols[1] and s.sh.shape[1] == P.sh_dim
-            sg.e_post = _lib.f32(s.e_post, "e_post", allow_none=True)
+            sg.e_post = None if s.group in folded else _lib.f32(s.e_post, "e_post", allow_none=True)
             if s.gate is not None:
                 assert s.gate.n_agg == s.n1 - s.n0, "gate edge list must cover the segment's aggregation nodes"
                 sg.gate_rowptr = _lib.i32(s.gate.rowptr, "gate.rowptr")

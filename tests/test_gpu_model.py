@@ -238,3 +238,59 @@ def test_all_atom_model_vs_oracle(mode):
             assert torch.allclose(a.cpu(), b, atol=1e-4)      # confidences within 1e-4 (BASELINE.json)
         else:
             assert rel_err(a, b) < 1e-4
+
+
+@pytest.mark.gpu
+def test_e_post_fold_matches_kernel_path():
+    """The per-graph edge-embedding offset (rec_sigma_emb) folded into the node projection on the host equals the
+    kernel's own e_post path (cb_tp_segment.e_post)."""
+    import confidence_bootstrapping_b200.tensor_layers as tl
+    from functools import partial
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import set_time, t_to_sigma
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    from confidence_bootstrapping_b200.utils import get_model
+    from helpers import small_score_args
+    args = small_score_args()
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    model = get_model(args, dev, t_to_sigma=partial(t_to_sigma, args=args), no_parallel=True).eval()
+    dl = [make_complex(5 + i, 60, 14, all_atoms=False, lm_dim=0) for i in range(3)]
+    outs = []
+    for fold in (True, False):
+        tl.FOLD_E_POST = fold
+        try:
+            batch = Batch.from_data_list(dl).to(dev)
+            set_time(batch, None, 0.4, 0.4, 0.4, batch.num_graphs, False, False, dev)
+            with torch.no_grad():
+                outs.append(model(batch))
+        finally:
+            tl.FOLD_E_POST = True
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert rel_err(a, b) < 2e-6
+
+
+@pytest.mark.gpu
+def test_sampling_is_bit_reproducible():
+    """Same inputs + same injected noise => identical bits: no floating-point atomics anywhere on the path."""
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule
+    from confidence_bootstrapping_b200.sampling import randomize_position, sampling
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    args = score_model_args()
+    model, t2s, _ = _build(args, seed=3)
+    g = Batch.from_data_list([make_complex(78, 70, 15, all_atoms=False)])
+    np.random.seed(1)
+    torch.manual_seed(1)
+    dl0 = [copy.deepcopy(g) for _ in range(4)]
+    randomize_position(dl0, False, False, args.tr_sigma_max)
+    sched = get_t_schedule("expbeta", 6, 1, 1)
+    outs = []
+    for _ in range(3):
+        dl = copy.deepcopy(dl0)
+        with injected_noise(seed=5):
+            out, _ = sampling(data_list=dl, model=model, inference_steps=6, tr_schedule=sched, rot_schedule=sched,
+                              tor_schedule=sched, device=torch.device("cuda"), t_to_sigma=t2s, model_args=args, batch_size=4)
+        outs.append(torch.stack([d["ligand"].pos for d in out]))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
