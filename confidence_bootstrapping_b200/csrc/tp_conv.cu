@@ -748,18 +748,15 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         PH_MARK(0);
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         PH_MARK(10);
-        __syncthreads();                                   // gather(cur), cols(nxt), hbase visible to everyone
-        PH_MARK(1);
-        if (nxt.valid) issue_gather(nxt, buf ^ 1);         // overlaps everything below
-
-        PH_MARK(2);
         const float* xs = xs_of(buf);
         const float* shs = shs_of(buf);
         const float* es = es_of(buf);
         const float* Ps = ps_of(buf);
         const int ksteps = (n + 7) >> 3;
         // ---- hidden layer on the tensor core: pre[q][e] = sum_c W1e[q][c] * e_attr[e][c]  (M = 128 hidden lanes,
-        // N = KC edges, K = ne, 3xTF32); the edge-embedding rows of the chunk become the hi/lo B-operand tiles
+        // N = KC edges, K = ne, 3xTF32); the edge-embedding rows of the chunk become the hi/lo B-operand tiles.
+        // Every thread splits exactly the 16-byte pieces it copied itself (same index map as issue_gather), so this
+        // needs no barrier after the cp.async wait; the barrier below publishes the tiles to the MMA.
 #pragma unroll 1
         for (int i = tid; i < KC * (ne / 4); i += THREADS) {
             const int e = i / (ne / 4), c4 = i - e * (ne / 4);
@@ -774,7 +771,8 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             *reinterpret_cast<float4*>(Elo + off) = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
+        __syncthreads();                                   // gather(cur), cols(nxt), hbase, E / W1e tiles visible to everyone
+        PH_MARK(1);
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // descriptors differ only in the start-address field: advance it by one k-step (2 core matrices) per iteration
@@ -788,6 +786,8 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&h_bar)) : "memory");
         }
+        PH_MARK(2);
+        if (nxt.valid) issue_gather(nxt, buf ^ 1);         // overlaps everything below
         PH_MARK(3);
         // the F / H~ operand tiles are free once the previous chunk's MMAs completed; their latency has been overlapped with
         // the iterator, the gather issue and the hidden-layer MMA above (which only touch the E / W1e tiles and D_h)
