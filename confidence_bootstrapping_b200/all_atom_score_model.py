@@ -274,13 +274,17 @@ class TensorProductScoreModel(_CGModel):
             lig_part = lig_segments(g[0], NL) + [Segment(lr, lr_e, lr_sh, g[1], 0, NL, col_off=o_rec),
                                                  Segment(la, la_e, la_sh, g[2], 0, NL, col_off=o_atom)]
             if l < n_layers - 1:
+                # the last layer reads residue / atom rows only through the cross edges into the ligand: in the layer before
+                # it, residues (atoms) without a cross edge (empty row of `rl` / `al`) skip their intra-receptor updates
+                g_rec, g_atom = (rl, al) if l == n_layers - 2 else (None, None)
                 segs = lig_part + [
-                    Segment(st.rec_edges, st.rec_e, st.rec_sh, g[3], o_rec, o_atom, col_off=o_rec, e_post=rec_sigma_emb),
+                    Segment(st.rec_edges, st.rec_e, st.rec_sh, g[3], o_rec, o_atom, col_off=o_rec, e_post=rec_sigma_emb, gate=g_rec),
                     Segment(rl, rl_e, rl_sh, g[4], o_rec, o_atom, col_off=0),
-                    Segment(st.ra_edges, st.ra_e, st.ra_sh, g[5], o_rec, o_atom, col_off=o_atom, e_post=rec_sigma_emb),
-                    Segment(st.atom_edges, st.atom_e, st.atom_sh, g[6], o_atom, o_atom + NA, col_off=o_atom, e_post=rec_sigma_emb),
+                    Segment(st.ra_edges, st.ra_e, st.ra_sh, g[5], o_rec, o_atom, col_off=o_atom, e_post=rec_sigma_emb, gate=g_rec),
+                    Segment(st.atom_edges, st.atom_e, st.atom_sh, g[6], o_atom, o_atom + NA, col_off=o_atom, e_post=rec_sigma_emb,
+                            gate=g_atom),
                     Segment(al, al_e, al_sh, g[7], o_atom, o_atom + NA, col_off=0),
-                    Segment(st.ar_edges, st.ar_e, st.ar_sh, g[8], o_atom, o_atom + NA, col_off=o_rec, e_post=rec_sigma_emb)]
+                    Segment(st.ar_edges, st.ar_e, st.ar_sh, g[8], o_atom, o_atom + NA, col_off=o_rec, e_post=rec_sigma_emb, gate=g_atom)]
                 x = layer.run(x, segs, NL + NR + NA, ns, agg_graph=node_graph, residual=x, **cols)
             else:
                 x = layer.run(x, lig_part, NL, ns, agg_graph=node_graph, residual=x, **cols)
