@@ -367,6 +367,13 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
 }
 
+// cheaper split for the F tiles (values of both signs, so truncation does not bias the sums): hi = x truncated to
+// TF32, lo = x - hi exactly (the tensor core truncates lo's low bits); error ~2^-21 relative per product
+__device__ __forceinline__ void split_tf32_trunc(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = x - hi;
+}
+
 __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, int sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
@@ -454,17 +461,18 @@ struct FRowCtx {
 // four consecutive edges per 16-byte core-matrix row.  NT = register-resident terms evaluated (warp-uniform).
 template <int NT>
 __device__ __forceinline__ void f_row(const FRowCtx& c, const int (&t_xi)[MAXT], const int (&t_si)[MAXT], const float (&t_cf)[MAXT]) {
+    const int dx4 = 4 * c.dxp, s4 = 4 * c.S;
+    const float* xe = c.xs;      // first edge of the current 4-edge group
+    const float* se = c.shs;
 #pragma unroll 1
-    for (int e4 = 0; e4 < c.nq; ++e4) {
+    for (int e4 = 0; e4 < c.nq; ++e4, xe += dx4, se += s4) {
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int e = min(4 * e4 + j, c.n - 1);          // clamp: edges >= n are zeroed below
-            const float* xe = c.xs + e * c.dxp;
-            const float* se = c.shs + e * c.S;
+            // edges >= n read stale (possibly non-finite) staging rows: the select below discards them
             float acc = 0.0f;
 #pragma unroll
-            for (int t = 0; t < NT; ++t) acc = fmaf(t_cf[t] * xe[t_xi[t]], se[t_si[t]], acc);
+            for (int t = 0; t < NT; ++t) acc = fmaf(t_cf[t] * xe[j * c.dxp + t_xi[t]], se[j * c.S + t_si[t]], acc);
             v[j] = (4 * e4 + j < c.n) ? acc : 0.0f;
         }
         if (c.te0 - c.tb0 > MAXT) {   // rare long rows: finish from the shared-memory term table
@@ -480,10 +488,10 @@ __device__ __forceinline__ void f_row(const FRowCtx& c, const int (&t_xi)[MAXT],
             }
         }
         float4 hi, lo;
-        split_tf32(v[0], hi.x, lo.x);
-        split_tf32(v[1], hi.y, lo.y);
-        split_tf32(v[2], hi.z, lo.z);
-        split_tf32(v[3], hi.w, lo.w);
+        split_tf32_trunc(v[0], hi.x, lo.x);
+        split_tf32_trunc(v[1], hi.y, lo.y);
+        split_tf32_trunc(v[2], hi.z, lo.z);
+        split_tf32_trunc(v[3], hi.w, lo.w);
         *reinterpret_cast<float4*>(c.Fhi + c.rbase + e4 * LBO) = hi;   // 4 consecutive edges = one 16-byte core-matrix row
         *reinterpret_cast<float4*>(c.Flo + c.rbase + e4 * LBO) = lo;
     }
@@ -947,11 +955,14 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     __syncwarp();
                     const int sub = lane >> 3, ch = (lane & 7) * 4;
                     if (c0 + ch < HA) {
+                        const int r0 = mt * 128 + lg * 32 + sub;       // this lane's rows: r0, r0 + 4, ...
+                        float* dst = Aout + (size_t)r0 * row_stride + c0 + ch;
+                        const float* src = stg + sub * STG_LD + ch;
+                        const int nr = min(8, (n_rows - r0 + 3) >> 2);  // rows of the lane inside the tile
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int rl = 4 * i + sub, rr = mt * 128 + lg * 32 + rl;
-                            if (rr < n_rows)
-                                *reinterpret_cast<float4*>(Aout + (size_t)rr * row_stride + c0 + ch) = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ch);
+                            if (i < nr) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src + i * 4 * STG_LD);
+                            dst += 4 * (size_t)row_stride;
                         }
                     }
                     __syncwarp();
