@@ -386,8 +386,9 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_addr(smem_u32(bar), parity); }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {   // addr = shared-space address of the barrier
 #pragma unroll 1
     for (int spin = 0; spin < (1 << 26); ++spin) {
         uint32_t ok;
@@ -1056,6 +1057,7 @@ __device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, uin
 template <int MT>
 __device__ __forceinline__ void row_fma(const float* const (&ap)[NT], const float* __restrict__ Wb, int HA, int a4, int kc, int nvalid,
                                         float (&acc)[NT][MTMAX]) {
+    // a4 <= KSTRIDE for every shipped layer (H <= 108): the loop body runs at most once per thread
 #pragma unroll 1
     for (int k = kc; k < a4; k += KSTRIDE) {
         float4 av[NT];
@@ -1077,7 +1079,7 @@ __device__ __forceinline__ void row_fma(const float* const (&ap)[NT], const floa
 }
 
 struct ConsumerCtx {
-    float* sm; const int* items; const int* n_items; uint64_t* full_bar; uint64_t* empty_bar;
+    float* sm; const int* items; const int* n_items; uint32_t full_bar, empty_bar;   // barriers: shared-space addresses of [STAGES]
     int stage, a_stage, zero, n_active, HA, a4, nl, kc, lane;
     int rs; bool mine; int w_off, nvalid, row_begin, row_end, run_rs;
 };
@@ -1098,7 +1100,7 @@ __device__ __forceinline__ void run_groups(const ConsumerCtx& c, int& G, float (
         for (int rg = c.row_begin; rg < c.row_end; rg += c.run_rs, ++G) {
             const int s = G % STAGES;
             const float* Ab = c.sm + s * c.stage;
-            mbar_wait(&c.full_bar[s], (G / STAGES) & 1);
+            tc::mbar_wait_addr(c.full_bar + 8u * s, (G / STAGES) & 1);
             if (c.mine && rg + c.rs < c.row_end) {
                 const float* ap[NT];
 #pragma unroll
@@ -1106,7 +1108,7 @@ __device__ __forceinline__ void run_groups(const ConsumerCtx& c, int& G, float (
                 row_fma<MT>(ap, Ab + c.a_stage + c.w_off, c.HA, c.a4, c.kc, c.nvalid, acc);
             }
             __syncwarp();
-            if (c.lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&c.empty_bar[s])) : "memory");
+            if (c.lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c.empty_bar + 8u * s) : "memory");
         }
     }
 }
@@ -1229,7 +1231,7 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
             // combo -> (row of the group, first output of the thread tile)
             const int rs = run.rs == 2 ? combo : 0;
             const int m0 = run.rs == 2 ? 0 : combo * run.mt;
-            const ConsumerCtx cx{sm, items, n_items_s, full_bar, empty_bar, L.stage, L.a_stage, L.zero, n_active, HA, a4, nl, kc, lane,
+            const ConsumerCtx cx{sm, items, n_items_s, smem_u32(full_bar), smem_u32(empty_bar), L.stage, L.a_stage, L.zero, n_active, HA, a4, nl, kc, lane,
                                  rs, m0 < run.mul, (rs * run.mul + m0) * HA, run.mul - m0, run.row_begin, run.row_end, run.rs};
             switch (run.mt) {
                 case 2: run_groups<2>(cx, G, acc); break;
