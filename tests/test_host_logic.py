@@ -143,3 +143,37 @@ def test_collate_to_device_matches_host_collate():
             if torch.is_tensor(v):
                 assert v.dtype == w.dtype and torch.equal(v, w), (key, k)
     assert a.num_graphs == b.num_graphs == 3
+
+
+def _randomize_position_per_sample(data_list, tr_sigma_max):
+    """Literal restatement of utils/sampling.py:15-48 (per-sample loops), the checker for the batched version."""
+    from scipy.spatial.transform import Rotation as R
+    from confidence_bootstrapping_b200 import sampling as S
+    centre_pocket = data_list[0]["receptor"].pos.mean(dim=0)
+    for g in data_list:
+        upd = np.random.uniform(low=-np.pi, high=np.pi, size=int(g["ligand"].edge_mask.sum()))
+        bonds = g["ligand", "ligand"].edge_index.T[g["ligand"].edge_mask]
+        g["ligand"].pos = S._twist_numpy(g["ligand"].pos, bonds, S._mask_rotate_of(g), upd)
+    for g in data_list:
+        c = torch.mean(g["ligand"].pos, dim=0, keepdim=True)
+        rot = torch.from_numpy(R.random().as_matrix()).float()
+        g["ligand"].pos = (g["ligand"].pos - c) @ rot.T + centre_pocket
+        g["ligand"].pos += torch.normal(mean=0, std=tr_sigma_max, size=(1, 3))
+
+
+def test_randomize_position_batched_matches_per_sample_loop():
+    """randomize_position applies the geometry per topology group at once; same random draws, same poses as the
+    reference's per-sample loop (also for a list that mixes two ligands)."""
+    import copy
+    from confidence_bootstrapping_b200.sampling import randomize_position
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    a, b = make_complex(11, 30, 14, all_atoms=False, lm_dim=0), make_complex(12, 30, 9, all_atoms=False, lm_dim=0)
+    base = [copy.deepcopy(a) for _ in range(3)] + [copy.deepcopy(b)] + [copy.deepcopy(a) for _ in range(2)]
+    got, want = copy.deepcopy(base), copy.deepcopy(base)
+    np.random.seed(4); torch.manual_seed(4)
+    randomize_position(got, False, False, 10.0)
+    np.random.seed(4); torch.manual_seed(4)
+    _randomize_position_per_sample(want, 10.0)
+    for x, y in zip(got, want):
+        assert x["ligand"].pos.dtype == torch.float32
+        assert float((x["ligand"].pos - y["ligand"].pos).abs().max()) < 1e-4
