@@ -292,3 +292,36 @@ def test_tp_conv_gate_prunes_dead_outputs():
     # gated-out nodes only see group-1 edges; their mean is over those edges alone
     assert rel_err(gated[~keep], only_b[~keep]) < 1e-5
     assert not torch.equal(gated[~keep], full[~keep])
+
+
+@pytest.mark.gpu
+def test_tp_conv_workspace_chunking_is_exact():
+    """Layers whose accumulator workspace exceeds WORKSPACE_BYTES run in node chunks (node_begin/node_end of the
+    C-ABI call, workspace tiles counted from node_begin): same bits as the single-chunk call."""
+    import confidence_bootstrapping_b200.tensor_layers as tl
+    from confidence_bootstrapping_b200.graph import static_edges
+    from confidence_bootstrapping_b200.tensor_layers import Segment, TensorProductConvLayer
+    from helpers import randomize_norm_stats
+    torch.manual_seed(0)
+    layer = TensorProductConvLayer(SEQ[3], "1x0e + 1x1o", SEQ[3], 32, residual=True, batch_norm=True, hidden_features=96,
+                                   faster=True, edge_groups=2)
+    randomize_norm_stats(layer, seed=1)
+    layer = layer.eval().cuda()
+    n, e = 333, 4000                      # 333 nodes: chunk boundaries that are not multiples of the 32-node tile
+    x = torch.randn(n, 74, device="cuda")
+    ei_a, ei_b = _random_graph(3, n, e).cuda(), _random_graph(4, n, e // 2, n_out=200).cuda()
+    ea, eb = torch.randn(e, 32, device="cuda"), torch.randn(e // 2, 32, device="cuda")
+    sha = o3.spherical_harmonics([0, 1], torch.randn(e, 3), True, "component").cuda()
+    shb = o3.spherical_harmonics([0, 1], torch.randn(e // 2, 3), True, "component").cuda()
+    (la, pa), (lb, pb) = static_edges(ei_a, n), static_edges(ei_b, 200)
+    segs = [Segment(la, ea[pa].contiguous(), sha[pa].contiguous(), 0, 0, n),
+            Segment(lb, eb[pb].contiguous(), shb[pb].contiguous(), 1, 0, 200)]
+    old = tl.WORKSPACE_BYTES
+    try:
+        with torch.no_grad():
+            whole = layer.run(x, segs, n, 0, (0, 32), residual=x)
+            tl.WORKSPACE_BYTES = 6 << 20        # 6 MiB: about 65 accumulators per chunk => ~9 chunks
+            chunked = layer.run(x, segs, n, 0, (0, 32), residual=x)
+    finally:
+        tl.WORKSPACE_BYTES = old
+    assert torch.equal(whole, chunked)
