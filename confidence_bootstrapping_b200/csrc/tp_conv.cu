@@ -1028,7 +1028,7 @@ using tc::mbar_wait;
 using tc::smem_u32;
 
 struct Layout {
-    int a_stage, w_stage, stage, zero, part, outacc, items, total;   // floats
+    int a_stage, w_stage, stage, zero, part, outacc, items, owner, total;   // floats
 };
 __host__ __device__ inline Layout make_layout(int H, int d_out, int n_slots) {
     Layout L;
@@ -1041,6 +1041,7 @@ __host__ __device__ inline Layout make_layout(int H, int d_out, int n_slots) {
     L.part = o;   o += CWARPS * 8 * NT * MTMAX;
     L.outacc = o; o += (NB * d_out + 3) & ~3;
     L.items = o;  o += n_slots * NB;
+    L.owner = o;  o += d_out;
     L.total = o;
     return L;
 }
@@ -1121,6 +1122,7 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
     __shared__ SlotTable st;
     __shared__ int active[CB_MAX_SEGS], n_items_s[CB_MAX_SEGS], deg_tot[NB];
     __shared__ RunS run_s[MAX_RUNS];
+    __shared__ signed char run_split[MAX_RUNS];    // which CTA of the tile (blockIdx.y) processes the run
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1184,6 +1186,44 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
     }
     if (a.n_runs == 0) n_active = 0;
     __syncthreads();
+    // ---- small launches (few node tiles) split a tile's runs over gridDim.y CTAs: runs that feed the same output
+    // block stay together, every output channel is written by exactly one CTA (channels no run writes: CTA 0)
+    int* chan_owner = reinterpret_cast<int*>(sm + L.owner);
+    const int n_split = (int)gridDim.y, split = (int)blockIdx.y;
+    if (n_split == 1) {
+        for (int i = tid; i < d_out; i += TT) chan_owner[i] = 0;
+        for (int i = tid; i < a.n_runs; i += TT) run_split[i] = 0;
+    } else if (tid == 0) {
+        int* blk_of = reinterpret_cast<int*>(part);      // scratch: the reduction buffer is idle during set-up
+        int* blk_cost = blk_of + MAX_RUNS;
+        int* blk_split = blk_cost + MAX_RUNS;
+        int load[8] = {0, 0, 0, 0, 0, 0, 0, 0}, n_blk = 0;
+        for (int ri = 0; ri < a.n_runs; ++ri) {
+            int b = -1;
+            for (int rj = 0; rj < ri; ++rj)
+                if (run_s[rj].out_base == run_s[ri].out_base && run_s[rj].out_step == run_s[ri].out_step) b = blk_of[rj];
+            if (b < 0) { b = n_blk++; blk_cost[b] = 0; }
+            blk_of[ri] = b;
+            blk_cost[b] += (run_s[ri].row_end - run_s[ri].row_begin + run_s[ri].rs - 1) / run_s[ri].rs;   // row groups = chain length
+        }
+        for (int it = 0; it < n_blk; ++it) {        // heaviest block first onto the least loaded CTA
+            int best = -1;
+            for (int b = 0; b < n_blk; ++b)
+                if (blk_cost[b] >= 0 && (best < 0 || blk_cost[b] > blk_cost[best])) best = b;
+            int tgt = 0;
+            for (int k = 1; k < n_split; ++k)
+                if (load[k] < load[tgt]) tgt = k;
+            blk_split[best] = tgt;
+            load[tgt] += blk_cost[best];
+            blk_cost[best] = -1;
+        }
+        for (int o = 0; o < d_out; ++o) chan_owner[o] = 0;
+        for (int ri = 0; ri < a.n_runs; ++ri) {
+            run_split[ri] = (signed char)blk_split[blk_of[ri]];
+            for (int m = 0; m < run_s[ri].mul; ++m) chan_owner[run_s[ri].out_base + m * run_s[ri].out_step] = run_split[ri];
+        }
+    }
+    __syncthreads();
 
     // ---- group sequence: for every run, for every active slot, the run's rows in groups of run.rs rows.  The
     // partial sums of a run stay in registers across the slots (they add into the same output channels).
@@ -1194,6 +1234,7 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
             int G = 0;
 #pragma unroll 1
             for (int ri = 0; ri < a.n_runs; ++ri) {
+                if (run_split[ri] != split) continue;
                 const RunS run = run_s[ri];
 #pragma unroll 1
                 for (int k = 0; k < n_active; ++k) {
@@ -1227,6 +1268,7 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
         int G = 0;
 #pragma unroll 1
         for (int ri = 0; ri < a.n_runs; ++ri) {
+            if (run_split[ri] != split) continue;
             const RunS run = run_s[ri];
             // combo -> (row of the group, first output of the thread tile)
             const int rs = run.rs == 2 ? combo : 0;
@@ -1274,7 +1316,7 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
     for (int i = tid; i < NB * d_out; i += TT) {
         const int n = i / d_out, o = i - n * d_out;
         const int node = t0 + n;
-        if (node < a.node_end) {
+        if (node < a.node_end && chan_owner[o] == split) {
             float v = outacc[i] / (float)max(deg_tot[n], 1);
             if (a.bn_scale) v = fmaf(v, a.bn_scale[o], a.bn_shift[o]);
             if (a.residual && o < a.d_res) v += a.residual[(size_t)node * a.ld_res + o];
@@ -1401,7 +1443,10 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
         return CB_ERR_CUDA;
     }
     const int tiles = cb_div_up(a->node_end - a->node_begin, tf::NB);
-    tf::tp_transform_kernel<<<tiles, tf::TT, smem, st>>>(*a);
+    // launches with few node tiles are chains of row groups on a handful of SMs: split each tile's runs over up to 8 CTAs
+    int n_split = 1;
+    while (n_split < 8 && n_split < a->n_runs && tiles * n_split * 2 <= CB_NUM_SMS * 3) n_split *= 2;
+    tf::tp_transform_kernel<<<dim3(tiles, n_split), tf::TT, smem, st>>>(*a);
     CB_CHECK_LAUNCH("cb_tp_conv_forward(transform)");
     return CB_OK;
 }
