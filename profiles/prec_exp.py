@@ -1,3 +1,4 @@
+"""Layer-level accuracy of the two accumulate paths against the fp32 and fp64 oracle (run on the GPU box)."""
 import os, sys, copy, numpy as np, torch
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from helpers import randomize_norm_stats, rel_err
@@ -31,7 +32,7 @@ for (in_ir, sh_l, out_ir, faster, groups, nef, residual) in cases:
         lc = copy.deepcopy(layer).cuda()
         line = f"{out_ir[:14]:14s} g={groups} "
         if want64 is not None: line += f"oracle32-vs-64 {rel_err(want, want64):.2e} | "
-        for mode in (1, 3, 2):
+        for mode in (1, 2):   # 1 = fp32 FFMA accumulate, 2 = tcgen05 3xTF32 accumulate (default)
             tl.ACCUM_MODE = mode
             got = lc(x.cuda(), ei.cuda(), [e.cuda() for e in ea_list] if groups > 1 else ea.cuda(), sh.cuda(), out_nodes=n_out)
             line += f"mode{mode}: vs32 {rel_err(got, want):.2e}"
