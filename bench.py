@@ -242,6 +242,8 @@ def run_cb200(opts):
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py (cb200 arm) needs a CUDA device; there is no CPU fallback"
+    if world > 1:   # one process per GPU on one box: keep the host-side collate of the ranks from oversubscribing the cores
+        torch.set_num_threads(max(1, (os.cpu_count() or world) // world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
