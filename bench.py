@@ -203,7 +203,7 @@ class TpTimer:
                 parts.append(c.reshape(1))
             else:   # dead-output pruning: only the edges of gated-in aggregation nodes are processed (and counted)
                 deg = edges.rowptr[1:edges.n_agg + 1] - edges.rowptr[:edges.n_agg]
-                keep = gate.rowptr[1:gate.n_agg + 1] > gate.rowptr[:gate.n_agg]
+                keep = gate.bool() if torch.is_tensor(gate) else gate.rowptr[1:gate.n_agg + 1] > gate.rowptr[:gate.n_agg]
                 parts.append((deg * keep).sum().reshape(1).to(c.dtype))
         counts = torch.cat(parts)        # one tiny launch per K3 call
         self.records.append((s, e, dict(layer=meta["layer"], n_in=meta["n_in"], n_out=meta["n_out"], groups=meta["groups"], counts=counts),

@@ -40,7 +40,7 @@ class TpSegment(C.Structure):
         ("W1e", C.c_void_p), ("ldw1", C.c_int32),
         ("b1", C.c_void_p), ("W2a", C.c_void_p),
         ("n0", C.c_int32), ("n1", C.c_int32), ("col_off", C.c_int32), ("slot", C.c_int32),
-        ("gate_rowptr", C.c_void_p),
+        ("gate_rowptr", C.c_void_p), ("gate_mask", C.c_void_p),
     ]
 
 

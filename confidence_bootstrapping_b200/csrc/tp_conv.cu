@@ -71,6 +71,7 @@ __device__ __forceinline__ void seg_edges(const cb_tp_segment& sg, int node, int
     e0 = __ldg(sg.rowptr + i);
     e1 = __ldg(sg.rowptr + i + 1);
     if (sg.gate_rowptr != nullptr && __ldg(sg.gate_rowptr + i + 1) <= __ldg(sg.gate_rowptr + i)) e1 = e0;
+    if (sg.gate_mask != nullptr && __ldg(sg.gate_mask + i) == 0) e1 = e0;
 }
 __device__ __forceinline__ int seg_degree(const cb_tp_segment& sg, int node) {
     int e0, e1;

@@ -352,11 +352,10 @@ class TensorProductScoreModel(nn.Module):
         node_graph = torch.cat([st.lig_batch, st.rec_batch]).contiguous()
         g = (0, 1, 2, 3) if self.differentiate_convolutions else (0, 0, 0, 0)
         n_layers = len(self.conv_layers)
+        gates = self._dead_output_gates(st, rl, n_layers)
         for l, layer in enumerate(self.conv_layers):
             if l < n_layers - 1:
-                # the last layer reads receptor rows only through rec->lig cross edges, so in the layer before it only
-                # receptors with a cross edge (= a non-empty row of the flipped list `rl`) need their rec->rec update
-                gate = rl if l == n_layers - 2 else None
+                gate = gates.get(l)
                 segs = lig_segments(g[0], NL) + [
                     Segment(lr, lr_attr, lr_sh, g[1], 0, NL, col_off=NL),
                     Segment(st.rec_edges, st.rec_e_attr, st.rec_sh, g[2], NL, NL + NR, col_off=NL, e_post=rec_sigma_emb, gate=gate),
@@ -372,6 +371,31 @@ class TensorProductScoreModel(nn.Module):
             return self._confidence_head(lig_x, st)
 
         return self._score_heads(data, st, emb, lig_x, lig_pos, sigma_emb, tr_sigma, rot_sigma, tor_sigma)
+
+    @staticmethod
+    def _dead_output_gates(st, rl, n_layers, hops=2):
+        """Receptor rows whose rec->rec update nobody reads, per conv layer (exact pruning, no approximation).
+        The last layer only updates ligand rows and reads receptor rows through the rec->lig cross edges, so the layer
+        before it needs the rec->rec update only for receptors with a cross edge (non-empty row of the flipped list
+        `rl`): keep set G0.  One layer earlier the needed rows are G0 plus everything G0 reads through rec->rec edges
+        (G1 = G0 u N(G0)), and so on.  Returns {layer index: uint8 keep mask over the receptor nodes}."""
+        NR = st.NR
+        if n_layers < 2 or NR == 0:
+            return {}
+        keep = rl.rowptr[1:NR + 1] > rl.rowptr[:NR]
+        gates = {n_layers - 2: keep.to(torch.uint8)}
+        if st.rec_edges.cap > 0:
+            if getattr(st, "rec_row_long", None) is None:
+                st.rec_row_long, st.rec_col_long = st.rec_edges.row.long(), st.rec_edges.col.long()
+            for h in range(1, hops + 1):
+                l = n_layers - 2 - h
+                if l < 0:
+                    break
+                reads = torch.zeros(NR, dtype=torch.int32, device=keep.device)
+                reads.index_add_(0, st.rec_col_long, keep.index_select(0, st.rec_row_long).to(torch.int32))   # integer adds: exact
+                keep = keep | (reads > 0)
+                gates[l] = keep.to(torch.uint8)
+        return gates
 
     def _score_heads(self, data, st, emb, lig_x, lig_pos, sigma_emb, tr_sigma, rot_sigma, tor_sigma):
         ns, lmax, dev, B = self.ns, self.sh_lmax, st.dev, st.B

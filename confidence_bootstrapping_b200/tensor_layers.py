@@ -95,7 +95,8 @@ class Segment:
     n1: int = 0
     col_off: int = 0                     # offset of the neighbour node type inside x
     e_post: Optional[torch.Tensor] = None  # [B, ne]
-    gate: Optional["EdgeList"] = None      # aggregation nodes without an edge in `gate` are skipped (dead-output pruning)
+    gate: Optional[object] = None          # dead-output pruning: an EdgeList (nodes without an edge in it are skipped) or a
+                                           # uint8 keep mask over the aggregation nodes
     slot: Optional[int] = None           # segments sharing a slot share (n0, n1, group) and one accumulator
 
 
@@ -245,7 +246,11 @@ class TensorProductConvLayer(nn.Module):
             sg.e_attr, sg.sh = _lib.f32(s.e_attr, "e_attr"), _lib.f32(s.sh, "sh")
             assert s.e_attr.shape[1] == e_cols[1] and s.sh.shape[1] == P.sh_dim
             sg.e_post = None if s.group in folded else _lib.f32(s.e_post, "e_post", allow_none=True)
-            if s.gate is not None:
+            if torch.is_tensor(s.gate):
+                assert s.gate.dtype == torch.uint8 and s.gate.is_cuda and s.gate.is_contiguous() and s.gate.numel() == s.n1 - s.n0, \
+                    "gate mask must be a contiguous CUDA uint8 tensor over the segment's aggregation nodes"
+                sg.gate_mask = s.gate.data_ptr()
+            elif s.gate is not None:
                 assert s.gate.n_agg == s.n1 - s.n0, "gate edge list must cover the segment's aggregation nodes"
                 sg.gate_rowptr = _lib.i32(s.gate.rowptr, "gate.rowptr")
             if s.group in P_agg:

@@ -152,6 +152,7 @@ typedef struct {
     const int32_t* gate_rowptr; /* optional [n1-n0+1] CSR row pointer of ANOTHER edge list over the same node range: nodes
                                with no edge there are skipped (treated as degree 0) -- dead-output pruning, e.g. receptor
                                rows of the last full conv layer that no rec->lig edge reads (score_model.py:372-374) */
+    const uint8_t* gate_mask;   /* optional [n1-n0] keep flags with the same effect (0 = skip the node in this segment)   */
 } cb_tp_segment;
 #define CB_MAX_SEGS 12
 typedef struct {

@@ -294,3 +294,35 @@ def test_sampling_is_bit_reproducible():
                               tor_schedule=sched, device=torch.device("cuda"), t_to_sigma=t2s, model_args=args, batch_size=4)
         outs.append(torch.stack([d["ligand"].pos for d in out]))
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.gpu
+def test_dead_output_gates_do_not_change_the_scores():
+    """The per-layer receptor keep masks (score_model._dead_output_gates) only skip rows nobody reads: the scores are
+    bit-identical with and without them."""
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import set_time
+    from confidence_bootstrapping_b200.score_model import TensorProductScoreModel
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    args = score_model_args()
+    model, t2s, _ = _build(args, seed=4)
+    dl = [make_complex(30 + i, 120 + 40 * i, 12 + 3 * i, all_atoms=False) for i in range(3)]
+    outs, kept = [], []
+    orig = TensorProductScoreModel._dead_output_gates
+    for use in (True, False):
+        def gates(st, rl, n_layers, hops=2, _use=use):
+            g = orig(st, rl, n_layers, hops) if _use else {}
+            kept.append({k: float(v.float().mean()) for k, v in g.items()})
+            return g
+        TensorProductScoreModel._dead_output_gates = staticmethod(gates)
+        try:
+            batch = Batch.from_data_list(dl).to("cuda")
+            set_time(batch, None, 0.05, 0.05, 0.05, batch.num_graphs, False, False, torch.device("cuda"))   # small sigma: short cross cutoff
+            with torch.no_grad():
+                outs.append(model(batch))
+        finally:
+            TensorProductScoreModel._dead_output_gates = orig
+    assert kept[0] and min(kept[0].values()) < 1.0, kept       # something was actually pruned
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert torch.equal(a, b)
