@@ -108,6 +108,11 @@ def _check(code: int, what: str):
 
 
 def _ptr(t, dtype, name, allow_none=False):
+    try:                                            # fast path: the common case is a valid tensor
+        if t.dtype is dtype and t.is_cuda and t.is_contiguous():
+            return t.data_ptr()
+    except AttributeError:
+        pass
     if t is None:
         if allow_none:
             return None
@@ -118,9 +123,7 @@ def _ptr(t, dtype, name, allow_none=False):
         raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (the cb200 kernels have no CPU path)")
-    if not t.is_contiguous():
-        raise RuntimeError(f"{name}: expected a contiguous tensor")
-    return t.data_ptr()
+    raise RuntimeError(f"{name}: expected a contiguous tensor")
 
 
 def f32(t, name, allow_none=False):
@@ -136,7 +139,8 @@ def u8(t, name, allow_none=False):
 
 
 def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw handle of torch's current stream on the current device (every cb200 kernel is enqueued on it)."""
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def _launched(n=1):

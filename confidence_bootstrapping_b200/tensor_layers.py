@@ -141,16 +141,27 @@ class TensorProductConvLayer(nn.Module):
         self.batch_norm = EquivariantBatchNorm(out_irreps) if batch_norm else None
         self._dev_prog = None
         self._w2a_cache = {}
+        self._param_cache = {}
+        self._proj_cache = {}
 
     # ------------------------------------------------------------------ helpers
     def _fc(self, g):
         return self.fc if self.edge_groups == 1 else self.fc[g]
 
+    def _params(self, g):
+        """(W1, b1, W2, b2) Parameters of the radial MLP of group g (looked up once: nn.Module attribute access is slow
+        and .to()/.cuda()/load_state_dict keep the Parameter objects)."""
+        hit = self._param_cache.get(g)
+        if hit is None:
+            fc = self._fc(g)
+            hit = self._param_cache[g] = (fc[0].weight, fc[0].bias, fc[3].weight, fc[3].bias)
+        return hit
+
     def _w2a(self, g):
         """Second Linear of the radial MLP with its bias folded in: [weight_numel, H+4] rows (W2[w], b2[w], 0, 0, 0),
         the layout the transform kernel streams with contiguous bulk copies.  Rebuilt when the parameters change."""
-        W2, b2 = self._fc(g)[3].weight, self._fc(g)[3].bias
-        key = (W2.data_ptr(), W2._version, b2.data_ptr(), b2._version, W2.device)
+        _, _, W2, b2 = self._params(g)
+        key = (W2.data_ptr(), W2._version, b2.data_ptr(), b2._version)
         hit = self._w2a_cache.get(g)
         if hit is None or hit[0] != key:
             with torch.no_grad():
@@ -159,6 +170,20 @@ class TensorProductConvLayer(nn.Module):
                 t[:, W2.shape[1]] = b2
             hit = (key, t)
             self._w2a_cache[g] = hit
+        return hit[1]
+
+    def _projection(self, groups, cols):
+        """[width, H * len(groups)] = the (offset, width) column block of every group's first Linear, transposed and
+        concatenated: the node-level projections of a call are one GEMM with it.  Rebuilt when a weight changes."""
+        ws = [self._params(g)[0] for g in groups]
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        ck = (groups, cols)
+        hit = self._proj_cache.get(ck)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                t = torch.cat([w[:, cols[0]:cols[0] + cols[1]] for w in ws], 0).t().contiguous()
+            hit = (key, t)
+            self._proj_cache[ck] = hit
         return hit[1]
 
     def device_program(self, device):
@@ -187,19 +212,17 @@ class TensorProductConvLayer(nn.Module):
         P = self.program
         dp = self.device_program(dev)
         H = self.hidden_features
-        groups = sorted({s.group for s in segments})
+        groups = tuple(sorted({s.group for s in segments}))
         # node-level projections of the first Linear (plain GEMM: plumbing)
         xs = x[:, :ns]
         P_nbr, P_agg = {}, {}
         if nbr_cols is not None:
-            Wn = torch.cat([self._fc(g)[0].weight[:, nbr_cols[0]:nbr_cols[0] + nbr_cols[1]] for g in groups], 0)
-            pn = (xs @ Wn.t()).contiguous()
+            pn = xs @ self._projection(groups, tuple(nbr_cols))
             for k, g in enumerate(groups):
                 P_nbr[g] = (pn, k * H)
         if agg_cols is not None:
-            Wa = torch.cat([self._fc(g)[0].weight[:, agg_cols[0]:agg_cols[0] + agg_cols[1]] for g in groups], 0)
             src = xs if agg_scalars is None else agg_scalars
-            pa = (src @ Wa.t()).contiguous()
+            pa = src @ self._projection(groups, tuple(agg_cols))
             for k, g in enumerate(groups):
                 P_agg[g] = (pa, k * H)
         # per-graph edge-embedding offsets (e_post) are constant per aggregation node: fold W1e.e_post[graph(node)] into the
@@ -217,7 +240,7 @@ class TensorProductConvLayer(nn.Module):
                 if graph_l is None:
                     graph_l = agg_graph.long()
                 t, off = P_agg[s.group]
-                W1e = self._fc(s.group)[0].weight[:, e_cols[0]:e_cols[0] + e_cols[1]]
+                W1e = self._params(s.group)[0][:, e_cols[0]:e_cols[0] + e_cols[1]]
                 t[s.n0:s.n1, off:off + H] += (s.e_post @ W1e.t()).index_select(0, graph_l[s.n0:s.n1])
                 folded.add(s.group)
         out = torch.empty((n_out, P.d_out), dtype=torch.float32, device=dev)
@@ -239,8 +262,8 @@ class TensorProductConvLayer(nn.Module):
             slot_ids.append(slot_ids[-1] + (key != prev) if slot_ids else 0)
             prev = key
         for k, s in enumerate(segments):
-            fc = self._fc(s.group)
-            W1, b1, W2a = fc[0].weight, fc[0].bias, self._w2a(s.group)
+            W1, b1 = self._params(s.group)[:2]
+            W2a = self._w2a(s.group)
             sg = a.segs[k]
             sg.rowptr, sg.col = _lib.i32(s.edges.rowptr, "rowptr"), _lib.i32(s.edges.col, "col")
             sg.e_attr, sg.sh = _lib.f32(s.e_attr, "e_attr"), _lib.f32(s.sh, "sh")
@@ -270,7 +293,7 @@ class TensorProductConvLayer(nn.Module):
             a.residual, a.d_res, a.ld_res = _lib.f32(residual, "residual"), min(residual.shape[1], P.d_out), residual.shape[1]
         a.out = out.data_ptr()
         # bookkeeping for profilers (bench.py): which edge counters / sizes this launch covers
-        a._meta = dict(layer=self, n_in=int(x.shape[0]), n_out=int(n_out), groups=groups,
+        a._meta = dict(layer=self, n_in=int(x.shape[0]), n_out=int(n_out), groups=list(groups),
                        edge_counters=[s.edges.n_edges_dev for s in segments],
                        edge_gates=[(s.edges, s.gate) for s in segments])
         # workspace: one R x (H+4) accumulator per (node, slot); process the nodes in chunks if it would be huge
