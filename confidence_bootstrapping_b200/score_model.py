@@ -373,7 +373,7 @@ class TensorProductScoreModel(nn.Module):
         return self._score_heads(data, st, emb, lig_x, lig_pos, sigma_emb, tr_sigma, rot_sigma, tor_sigma)
 
     @staticmethod
-    def _dead_output_gates(st, rl, n_layers, hops=2):
+    def _dead_output_gates(st, rl, n_layers, hops=4):
         """Receptor rows whose rec->rec update nobody reads, per conv layer (exact pruning, no approximation).
         The last layer only updates ligand rows and reads receptor rows through the rec->lig cross edges, so the layer
         before it needs the rec->rec update only for receptors with a cross edge (non-empty row of the flipped list

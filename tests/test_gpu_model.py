@@ -311,7 +311,7 @@ def test_dead_output_gates_do_not_change_the_scores():
     outs, kept = [], []
     orig = TensorProductScoreModel._dead_output_gates
     for use in (True, False):
-        def gates(st, rl, n_layers, hops=2, _use=use):
+        def gates(st, rl, n_layers, hops=4, _use=use):
             g = orig(st, rl, n_layers, hops) if _use else {}
             kept.append({k: float(v.float().mean()) for k, v in g.items()})
             return g
