@@ -180,7 +180,7 @@ def workload_config(confidence):
 # ----------------------------------------------------------------------------------------- cb200 arm
 # dram__bytes_read.sum + dram__bytes_write.sum of the two K3 kernels for the 74->74 conv layer of the bench workload
 # (ncu --set full, profiles/r1/k3_ncu_summary.txt); refreshed whenever the kernels change
-K3_DRAM_BYTES_PER_CALL = 4.91e9   # 2.52 GB accumulate (2.33 GB written) + 2.40 GB transform (2.37 GB read)
+K3_DRAM_BYTES_PER_CALL = 4.36e9   # 2.24 GB accumulate (2.06 GB written) + 2.12 GB transform (2.10 GB read), dead-output gate active
 
 
 class TpTimer:
