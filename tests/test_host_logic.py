@@ -177,3 +177,37 @@ def test_randomize_position_batched_matches_per_sample_loop():
     for x, y in zip(got, want):
         assert x["ligand"].pos.dtype == torch.float32
         assert float((x["ligand"].pos - y["ligand"].pos).abs().max()) < 1e-4
+
+
+def test_dead_output_gates_are_k_hop_closures():
+    """score_model._dead_output_gates: layer n-2 keeps the receptors with a cross edge, layer n-2-k additionally everything
+    those read through k rec->rec hops (checked against a brute-force reachability on a random graph)."""
+    from types import SimpleNamespace
+    from confidence_bootstrapping_b200.graph import EdgeList
+    from confidence_bootstrapping_b200.score_model import TensorProductScoreModel
+    g = torch.Generator().manual_seed(0)
+    NR, E = 60, 150
+    row = torch.randint(0, NR, (E,), generator=g)      # aggregation node reads col
+    col = torch.randint(0, NR, (E,), generator=g)
+    order = torch.argsort(row, stable=True)
+    row, col = row[order], col[order]
+    rowptr = torch.zeros(NR + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(torch.bincount(row, minlength=NR), 0).to(torch.int32)
+    rec_edges = EdgeList(rowptr, row.to(torch.int32), col.to(torch.int32), E, NR)
+    has_cross = torch.zeros(NR, dtype=torch.bool)
+    has_cross[torch.randperm(NR, generator=g)[:6]] = True
+    rl_ptr = torch.zeros(NR + 1, dtype=torch.int32)
+    rl_ptr[1:] = torch.cumsum(has_cross.int() * 3, 0).to(torch.int32)
+    rl = EdgeList(rl_ptr, torch.zeros(1, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), int(rl_ptr[-1]), NR)
+    st = SimpleNamespace(NR=NR, rec_edges=rec_edges, rec_row_long=None, rec_col_long=None)
+    gates = TensorProductScoreModel._dead_output_gates(st, rl, n_layers=6, hops=4)
+    assert sorted(gates) == [0, 1, 2, 3, 4]
+    keep = has_cross.clone()
+    for k, layer in enumerate([4, 3, 2, 1, 0]):
+        assert torch.equal(gates[layer].bool(), keep), layer
+        nxt = keep.clone()
+        for r, c in zip(row.tolist(), col.tolist()):
+            if keep[r]:
+                nxt[c] = True
+        keep = nxt
+    assert TensorProductScoreModel._dead_output_gates(st, rl, n_layers=1) == {}
