@@ -1080,6 +1080,40 @@ __device__ __forceinline__ void row_fma(const float* const (&ap)[NT], const floa
     }
 }
 
+// Packed-FMA variant for thread tiles of at most 8 outputs (mul <= 8 runs: 5 of every 6 rows).  Blackwell's FFMA2
+// (fma.rn.f32x2) does two independent fp32 FMAs per issue slot; the even and the odd K columns of a chunk accumulate in the
+// two halves of one register pair, acc[j][2m] / acc[j][2m+1], which the run-end reduction adds.  Same IEEE fp32 FMAs, half
+// the FMA instructions.
+__device__ __forceinline__ void fma2(float& a0, float& a1, float x0, float x1, float y0, float y1) {
+    unsigned long long a, x, y;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(y0), "f"(y1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(x), "l"(y));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+
+template <int MT>
+__device__ __forceinline__ void row_fma2(const float* const (&ap)[NT], const float* __restrict__ Wb, int HA, int a4, int kc, int nvalid,
+                                         float (&acc)[NT][MTMAX]) {
+    static_assert(2 * MT <= MTMAX, "pair accumulators need two slots per output");
+#pragma unroll 1
+    for (int k = kc; k < a4; k += KSTRIDE) {
+        float4 av[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) av[j] = *reinterpret_cast<const float4*>(ap[j] + 4 * k);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const float4 w = *reinterpret_cast<const float4*>(Wb + (m < nvalid ? m : 0) * HA + 4 * k);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                fma2(acc[j][2 * m], acc[j][2 * m + 1], av[j].x, av[j].y, w.x, w.y);
+                fma2(acc[j][2 * m], acc[j][2 * m + 1], av[j].z, av[j].w, w.z, w.w);
+            }
+        }
+    }
+}
+
 struct ConsumerCtx {
     float* sm; const int* items; const int* n_items; uint32_t full_bar, empty_bar;   // barriers: shared-space addresses of [STAGES]
     int stage, a_stage, zero, n_active, HA, a4, nl, kc, lane;
@@ -1107,7 +1141,8 @@ __device__ __forceinline__ void run_groups(const ConsumerCtx& c, int& G, float (
                 const float* ap[NT];
 #pragma unroll
                 for (int j = 0; j < NT; ++j) ap[j] = a_off[j] >= 0 ? Ab + a_off[j] : c.sm + c.zero;
-                row_fma<MT>(ap, Ab + c.a_stage + c.w_off, c.HA, c.a4, c.kc, c.nvalid, acc);
+                if constexpr (2 * MT <= MTMAX) row_fma2<MT>(ap, Ab + c.a_stage + c.w_off, c.HA, c.a4, c.kc, c.nvalid, acc);
+                else row_fma<MT>(ap, Ab + c.a_stage + c.w_off, c.HA, c.a4, c.kc, c.nvalid, acc);
             }
             __syncwarp();
             if (c.lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c.empty_bar + 8u * s) : "memory");
@@ -1291,7 +1326,8 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
 #pragma unroll
                 for (int m = 0; m < MTMAX; ++m) {
                     if (m < run.mt) {       // uniform
-                        float v = acc[j][m];
+                        // thread tiles of <= 8 outputs keep even / odd K columns in two slots per output (row_fma2)
+                        float v = 2 * run.mt <= MTMAX ? acc[j][(2 * m) % MTMAX] + acc[j][(2 * m + 1) % MTMAX] : acc[j][m];
                         v += __shfl_xor_sync(0xffffffffu, v, 8);
                         v += __shfl_xor_sync(0xffffffffu, v, 16);
                         if (lane < 8) part[((warp * 8 + nl) * NT + j) * MTMAX + m] = v;
