@@ -150,20 +150,26 @@ def _replicated(vals):
     """True when every tensor of the list has the same content (the N copies of one complex that
     inference.py / finetune_train.py make with copy.deepcopy share everything but the ligand pose)."""
     v0 = vals[0]
-    if len(vals) < 2 or v0.device.type != "cpu" or v0.numel() < 1024:
+    if len(vals) < 2 or v0.device.type != "cpu" or v0.numel() == 0:
         return False
     return all(v.shape == v0.shape and v.dtype == v0.dtype and (v.data_ptr() == v0.data_ptr() or torch.equal(v, v0)) for v in vals[1:])
 
 
-def _cat0(vals, device):
+def _cat0(vals, device, rep_out=None):
     """torch.cat(vals, 0), landing on `device` when given.  Replicated host tensors cross the bus once and are
-    tiled on the device."""
+    tiled on the device.  `rep_out` (a list) receives whether the values were identical copies."""
     if device is None:
+        if rep_out is not None:
+            rep_out.append(False)        # unknown: the host path does not compare
         return torch.cat(vals, 0)
     if _replicated(vals):
+        if rep_out is not None:
+            rep_out.append(True)
         _count_h2d(vals[0], device)
         d = vals[0].to(device, non_blocking=True)
         return d.repeat((len(vals),) + (1,) * (d.dim() - 1))
+    if rep_out is not None:
+        rep_out.append(len(vals) < 2)
     out = torch.cat(vals, 0)
     _count_h2d(out, device)
     return out.to(device, non_blocking=True)
@@ -182,13 +188,15 @@ class Batch(HeteroData):
             counts[nt] = [d[nt].num_nodes for d in data_list]
         offs = {nt: np.concatenate([[0], np.cumsum(c)]) for nt, c in counts.items()}
         slices: Dict[Any, Dict[str, List[int]]] = {}
+        rep_flags: Dict[Any, List[bool]] = {}      # per store: were the concatenated attributes identical copies?
         for nt in first.node_types:
             st = b[nt]
             slices[nt] = {}
+            rep_flags[nt] = []
             for k in first[nt].keys():
                 vals = [d[nt]._d[k] for d in data_list]
                 if _is_cat_tensor(vals[0]):
-                    st._d[k] = _cat0(vals, device)
+                    st._d[k] = _cat0(vals, device, rep_flags[nt])
                     slices[nt][k] = [0] + list(np.cumsum([v.shape[0] for v in vals]))
                 else:
                     st._d[k] = vals
@@ -199,10 +207,12 @@ class Batch(HeteroData):
         for et in first.edge_types:
             st = b[et]
             slices[et] = {}
+            rep_flags[et] = []
             for k in first[et].keys():
                 vals = [d[et]._d[k] for d in data_list]
                 if k == "edge_index":
-                    if device is not None and _replicated(vals):
+                    rep_flags[et].append(device is not None and _replicated(vals))
+                    if rep_flags[et][-1]:
                         _count_h2d(vals[0], device)
                         shifts = torch.tensor(np.stack([offs[et[0]][:n], offs[et[2]][:n]], 1), dtype=vals[0].dtype).to(device)
                         st._d[k] = (vals[0].to(device).unsqueeze(0) + shifts.unsqueeze(2)).permute(1, 0, 2).reshape(2, -1)
@@ -215,7 +225,7 @@ class Batch(HeteroData):
                             st._d[k] = st._d[k].to(device)
                     slices[et][k] = [0] + list(np.cumsum([v.shape[1] for v in vals]))
                 elif _is_cat_tensor(vals[0]):
-                    st._d[k] = _cat0(vals, device)
+                    st._d[k] = _cat0(vals, device, rep_flags[et])
                     slices[et][k] = [0] + list(np.cumsum([v.shape[0] for v in vals]))
                 else:
                     st._d[k] = vals
@@ -232,6 +242,12 @@ class Batch(HeteroData):
                     b._g[k] = b._g[k].to(device)
             else:
                 b._g[k] = vals
+        # node types whose attributes AND intra-type edges are identical in every graph (the N copies of one complex):
+        # models may compute pose-independent quantities of such a type once and tile them
+        b._g["_replicated_types"] = sorted(
+            nt for nt in first.node_types
+            if n > 1 and rep_flags[nt] and all(rep_flags[nt])
+            and all(all(rep_flags[et]) and rep_flags[et] for et in first.edge_types if et[0] == nt and et[2] == nt))
         b._g["_num_graphs"] = n
         b._g["_slices"] = slices
         b._g["_offs"] = offs

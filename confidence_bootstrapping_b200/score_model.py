@@ -279,11 +279,25 @@ class TensorProductScoreModel(nn.Module):
         emb = self._embedders()
         zero_sigma = None
         rec_e_attr, rec_sh = emb.rec(st.rec_edges, st.rec_pos, st.rec_pos, st.rec_batch, zero_sigma, self.sh_lmax)
-        x = self.rec_node_embedding(st.rec_x)
         ns = self.ns
-        for layer in self.rec_emb_layers:
-            seg = Segment(st.rec_edges, rec_e_attr, rec_sh, 0, 0, st.NR)
-            x = layer.run(x.contiguous(), [seg], st.NR, ns, (0, ns), (ns, ns), (2 * ns, ns), residual=x.contiguous())
+        n_rec_edges = st.rec_edges.cap
+        if ("receptor" in getattr(data, "_g", {}).get("_replicated_types", ()) and B > 1 and st.NR % B == 0
+                and n_rec_edges % B == 0 and n_rec_edges > 0):
+            # the batch holds B copies of one receptor (flagged by the collate): its pose-independent embedding is computed
+            # for the first copy and tiled.  Graph 0 owns the first NR/B nodes and, the static edge list being sorted by
+            # aggregation node, the first E/B edges.
+            n0, e0 = st.NR // B, n_rec_edges // B
+            e_first = EdgeList(st.rec_edges.rowptr[:n0 + 1], st.rec_edges.row[:e0], st.rec_edges.col[:e0], e0, n0)
+            x = self.rec_node_embedding(st.rec_x[:n0])
+            for layer in self.rec_emb_layers:
+                seg = Segment(e_first, rec_e_attr[:e0], rec_sh[:e0], 0, 0, n0)
+                x = layer.run(x.contiguous(), [seg], n0, ns, (0, ns), (ns, ns), (2 * ns, ns), residual=x.contiguous())
+            x = x.repeat(B, 1)
+        else:
+            x = self.rec_node_embedding(st.rec_x)
+            for layer in self.rec_emb_layers:
+                seg = Segment(st.rec_edges, rec_e_attr, rec_sh, 0, 0, st.NR)
+                x = layer.run(x.contiguous(), [seg], st.NR, ns, (0, ns), (ns, ns), (2 * ns, ns), residual=x.contiguous())
         st.rec_node_attr, st.rec_e_attr, st.rec_sh = x.contiguous(), rec_e_attr, rec_sh
         rec.cb200_static = {"owner": id(self), "static": st}
         return st

@@ -322,7 +322,34 @@ def test_dead_output_gates_do_not_change_the_scores():
             with torch.no_grad():
                 outs.append(model(batch))
         finally:
-            TensorProductScoreModel._dead_output_gates = orig
+            TensorProductScoreModel._dead_output_gates = staticmethod(orig)
     assert kept[0] and min(kept[0].values()) < 1.0, kept       # something was actually pruned
     for a, b in zip(outs[0][:3], outs[1][:3]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_replicated_receptor_embedding_is_tiled():
+    """A batch collated on the device from N copies of one complex carries the 'receptor is replicated' flag; the score
+    model then embeds the receptor once and tiles it.  Same scores as the per-copy embedding."""
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import set_time
+    from confidence_bootstrapping_b200.sampling import randomize_position
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    args = score_model_args()
+    model, t2s, _ = _build(args, seed=5)
+    g = Batch.from_data_list([make_complex(41, 350, 18, all_atoms=False)])
+    np.random.seed(2); torch.manual_seed(2)
+    dl = [copy.deepcopy(g) for _ in range(4)]
+    randomize_position(dl, False, False, args.tr_sigma_max)
+    outs = []
+    for device in ("cuda", None):
+        batch = Batch.from_data_list(copy.deepcopy(dl), device=device)
+        assert ("receptor" in batch._g["_replicated_types"]) == (device is not None)
+        batch = batch.to("cuda")
+        set_time(batch, None, 0.3, 0.3, 0.3, batch.num_graphs, False, False, torch.device("cuda"))
+        with torch.no_grad():
+            outs.append(model(batch))
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert rel_err(a, b) < 1e-6

@@ -211,3 +211,17 @@ def test_dead_output_gates_are_k_hop_closures():
                 nxt[c] = True
         keep = nxt
     assert TensorProductScoreModel._dead_output_gates(st, rl, n_layers=1) == {}
+
+
+def test_collate_flags_replicated_node_types():
+    import copy
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    a, b = make_complex(3, 40, 12, all_atoms=True, lm_dim=8), make_complex(4, 40, 12, all_atoms=True, lm_dim=8)
+    same = [copy.deepcopy(a) for _ in range(3)]
+    for i, d in enumerate(same):
+        d["ligand"].pos = d["ligand"].pos + float(i)
+    flagged = Batch.from_data_list(same, device="cpu")._g["_replicated_types"]
+    assert "receptor" in flagged and "atom" in flagged and "ligand" not in flagged
+    assert Batch.from_data_list([copy.deepcopy(a), copy.deepcopy(b)], device="cpu")._g["_replicated_types"] == []
+    assert Batch.from_data_list(same)._g["_replicated_types"] == []      # the host collate does not compare
