@@ -39,3 +39,12 @@ def score_model_args(**overrides) -> Namespace:
 
 def confidence_model_args(**overrides) -> Namespace:
     return Namespace(**{**CONFIDENCE_MODEL_ARGS, **overrides})
+
+
+def all_atom_score_model_args(**overrides) -> Namespace:
+    """BASELINE.json config 5: the all-atom SCORE model.  The reference ships no YAML for it; the
+    benchmarked hyper-parameters are the confidence YAML's sizes (ns 24, nv 6, 5 conv layers, lmax 2 by default, no
+    receptor-embedding layers, 1280-d precomputed LM features) with the score YAML's diffusion ranges and heads."""
+    base = {**SCORE_MODEL_ARGS, "all_atoms": True, "ns": 24, "nv": 6, "num_conv_layers": 5, "num_prot_emb_layers": 0,
+            "sh_lmax": 2, "reduce_pseudoscalars": False, "embed_also_ligand": False, "embedding_scale": 10000}
+    return Namespace(**{**base, **overrides})

@@ -253,7 +253,38 @@ class Batch(HeteroData):
         b._g["_offs"] = offs
         return b
 
+    def _rebuild_slices(self):
+        """Slices / node offsets re-derived from the `batch` vectors (after an in-place edit such as crop_beyond changed
+        the number of nodes or edges per graph).  Edges belong to the graph of their first endpoint."""
+        n = self.num_graphs
+        counts = {}
+        for nt in self.node_types:
+            st = self._stores[nt]
+            counts[nt] = torch.bincount(st._d["batch"].long().cpu(), minlength=n).numpy() if "batch" in st else np.zeros(n, dtype=np.int64)
+        offs = {nt: np.concatenate([[0], np.cumsum(c)]) for nt, c in counts.items()}
+        slices = {}
+        for key, st in self._stores.items():
+            slices[key] = {}
+            if isinstance(key, tuple):
+                if "edge_index" not in st:
+                    continue
+                src = st._d["edge_index"][0].long().cpu()
+                ec = torch.bincount(torch.bucketize(src, torch.as_tensor(offs[key[0]][1:]), right=True), minlength=n).numpy()
+                sl = [0] + list(np.cumsum(ec))
+                for k, v in st.items():
+                    if k == "edge_index" or (_is_cat_tensor(v) and v.shape[0] == src.shape[0]):
+                        slices[key][k] = sl
+            else:
+                sl = [int(o) for o in offs[key]]
+                for k, v in st.items():
+                    if k not in ("batch", "ptr") and _is_cat_tensor(v) and v.shape[0] == sl[-1]:
+                        slices[key][k] = sl
+        self._g["_slices"], self._g["_offs"] = slices, offs
+        self._g["_slices_stale"] = False
+
     def to_data_list(self) -> List[HeteroData]:
+        if self._g.get("_slices_stale"):
+            self._rebuild_slices()
         n, slices, offs = self.num_graphs, self._g["_slices"], self._g["_offs"]
         out = []
         for i in range(n):

@@ -47,7 +47,7 @@ def gather_results(local_ids: Sequence[int], poses: Sequence[torch.Tensor], conf
     """All-gather per-complex results.
 
     local_ids[k] is the global index of the k-th local complex, poses[k] its [S, N_lig, 3] float32 final
-    coordinates, confidences[k] its [S] confidences (or None).  Every rank returns the full lists
+    coordinates, confidences[k] its [S] (or [S, k]) confidences (or None).  Every rank returns the full lists
     (index = global complex id).  Payload is KB-MB: one padded all_gather of a flat float buffer plus
     one of the int64 layout table; NCCL on GPUs, gloo for the CPU tests."""
     rank, world = _world()
@@ -58,10 +58,19 @@ def gather_results(local_ids: Sequence[int], poses: Sequence[torch.Tensor], conf
             out_p[i], out_c[i] = p, c
         return out_p, out_c
     if device is None:
-        device = poses[0].device if len(poses) else torch.device("cpu")
-    # layout rows: (global id, S, N, has_conf)
-    meta = torch.tensor([[i, p.shape[0], p.shape[1], int(c is not None)] for i, p, c in zip(local_ids, poses, confidences)],
-                        dtype=torch.int64, device=device).reshape(-1, 4)
+        if len(poses):
+            device = poses[0].device
+        elif dist.get_backend() == "nccl":     # a rank without complexes still joins the collectives with CUDA tensors
+            device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            device = torch.device("cpu")
+    # layout rows: (global id, S, N, confidence numel (0 = none), confidence trailing width)
+    def conf_meta(c):
+        if c is None:
+            return 0, 0
+        return int(c.numel()), (int(c.numel() // max(c.shape[0], 1)) if c.dim() > 1 else 0)
+    meta = torch.tensor([[i, p.shape[0], p.shape[1], *conf_meta(c)] for i, p, c in zip(local_ids, poses, confidences)],
+                        dtype=torch.int64, device=device).reshape(-1, 5)
     flat = [p.reshape(-1).float() for p in poses] + [c.reshape(-1).float() for c in confidences if c is not None]
     payload = torch.cat(flat) if flat else torch.zeros(0, device=device)
     sizes = torch.tensor([meta.shape[0], payload.numel()], dtype=torch.int64, device=device)
@@ -69,7 +78,7 @@ def gather_results(local_ids: Sequence[int], poses: Sequence[torch.Tensor], conf
     dist.all_gather(all_sizes, sizes)
     max_meta = max(int(s[0]) for s in all_sizes)
     max_pay = max(int(s[1]) for s in all_sizes)
-    meta_pad = torch.zeros((max(max_meta, 1), 4), dtype=torch.int64, device=device)
+    meta_pad = torch.zeros((max(max_meta, 1), 5), dtype=torch.int64, device=device)
     meta_pad[: meta.shape[0]] = meta
     pay_pad = torch.zeros(max(max_pay, 1), dtype=torch.float32, device=device)
     pay_pad[: payload.numel()] = payload
@@ -83,13 +92,14 @@ def gather_results(local_ids: Sequence[int], poses: Sequence[torch.Tensor], conf
         n_meta = int(all_sizes[r][0])
         rows = metas[r][:n_meta].tolist()
         off = 0
-        for (i, S, N, _) in rows:
+        for (i, S, N, _, _) in rows:
             out_p[i] = pays[r][off: off + S * N * 3].reshape(S, N, 3)
             off += S * N * 3
-        for (i, S, N, has_c) in rows:
-            if has_c:
-                out_c[i] = pays[r][off: off + S]
-                off += S
+        for (i, S, N, n_conf, k_conf) in rows:
+            if n_conf:      # [S] for a scalar head, [S, k] when rmsd_classification_cutoff is a list (utils/utils.py:262)
+                c = pays[r][off: off + n_conf]
+                out_c[i] = c.reshape(-1, k_conf) if k_conf else c
+                off += n_conf
     return out_p, out_c
 
 

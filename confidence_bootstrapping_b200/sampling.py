@@ -8,7 +8,9 @@ arithmetic of sampling.py:119-141 is folded into the K4 launch as scalar coeffic
 """
 from __future__ import annotations
 
+import contextlib
 import copy
+import warnings
 
 import numpy as np
 import torch
@@ -128,6 +130,46 @@ def _twist_numpy(pos, bonds, mask_rotate, updates):
     return torch.from_numpy(p.astype(np.float32))
 
 
+_warned_train_mode = False
+
+
+@contextlib.contextmanager
+def _inference_mode(*models):
+    """Scoped eval() around a sampling call, plus a refresh of the derived-weight caches.
+
+    CONSCIOUS DIVERGENCE: finetune_train.py:177 samples with the score model left in
+    train mode (dropout 0.1 active, e3nn BatchNorm on batch statistics) because nothing calls .eval() on that path;
+    inference.py:309, dock.py:101 and bootstrapping.py:106 do.  The cb200 kernels implement the inference arithmetic
+    (running-stat BatchNorm folded into the K3 epilogue, no dropout), so sampling() runs the models in eval mode and
+    restores their previous mode afterwards -- the caller's train_epoch (utils/training.py:185) sets .train() itself.
+    A one-time warning says so.  Without this the callers' `except Exception` retry loop (finetune_train.py:187-195)
+    would halve the batch five times and skip every complex."""
+    global _warned_train_mode
+    prev = []
+    for m in models:
+        if m is None or not isinstance(m, torch.nn.Module):
+            continue
+        prev.append((m, m.training))
+        if m.training:
+            if not _warned_train_mode:
+                warnings.warn("cb200 sampling(): the model is in train mode (the reference's finetune_train.py samples that way: "
+                              "dropout on, batch-statistic BatchNorm); cb200 samples in eval mode and restores train mode afterwards")
+                _warned_train_mode = True
+            m.eval()
+        # folded weights (W2a, projections, BatchNorm affine) are rebuilt per call: in-place `.data` writes
+        # (ExponentialMovingAverage.copy_to / restore between sampling calls) do not bump tensor versions
+        for sub in m.modules():
+            inv = getattr(sub, "invalidate_caches", None)
+            if inv is not None:
+                inv()
+    try:
+        yield
+    finally:
+        for m, was_training in prev:
+            if was_training:
+                m.train(True)
+
+
 def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma,
                       model_args, mask_rotate, noise_rows=None, no_random=False, ode=False, t_schedule=None,
                       no_final_step_noise=False, temp_sampling=(1.0, 1.0, 1.0), temp_psi=(0.0, 0.0, 0.0),
@@ -231,7 +273,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     g_const = {k: float(np.sqrt(np.float32(2 * np.log(getattr(model_args, f"{k}_sigma_max") / getattr(model_args, f"{k}_sigma_min")))))
                for k in ("tr", "rot", "tor")}
 
-    with torch.no_grad():
+    with torch.no_grad(), _inference_mode(model, confidence_model):
         for batch_id, batch in enumerate(loader):
             b = batch.num_graphs
             batch = batch.to(device)

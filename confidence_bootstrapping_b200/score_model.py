@@ -281,7 +281,7 @@ class TensorProductScoreModel(nn.Module):
         rec_e_attr, rec_sh = emb.rec(st.rec_edges, st.rec_pos, st.rec_pos, st.rec_batch, zero_sigma, self.sh_lmax)
         ns = self.ns
         n_rec_edges = st.rec_edges.cap
-        if ("receptor" in getattr(data, "_g", {}).get("_replicated_types", ()) and B > 1 and st.NR % B == 0
+        if ("receptor" in getattr(data, "_g", {}).get("_replicated_types", ()) and B > 1 and len(set(nr_h)) == 1
                 and n_rec_edges % B == 0 and n_rec_edges > 0):
             # the batch holds B copies of one receptor (flagged by the collate): its pose-independent embedding is computed
             # for the first copy and tiled.  Graph 0 owns the first NR/B nodes and, the static edge list being sorted by

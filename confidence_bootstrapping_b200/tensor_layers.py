@@ -70,6 +70,19 @@ class EquivariantBatchNorm(nn.Module):
                              persistent=False)
         self._affine_cache = None
 
+    def invalidate_caches(self):
+        """Forget the folded (scale, shift).  The cache key (data_ptr, _version) does not see writes through
+        `param.data.copy_()` (the reference's ExponentialMovingAverage.copy_to / restore, utils/utils.py:353-392)."""
+        self._affine_cache = None
+
+    def _apply(self, fn, *a, **kw):
+        self._affine_cache = None
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self._affine_cache = None
+        return super()._load_from_state_dict(*a, **kw)
+
     def affine(self):
         """(scale[d], shift[d]) such that eval-mode BN(x) = x * scale + shift, per feature channel.
         Cached until a parameter or running statistic changes."""
@@ -143,6 +156,29 @@ class TensorProductConvLayer(nn.Module):
         self._w2a_cache = {}
         self._param_cache = {}
         self._proj_cache = {}
+
+    # ------------------------------------------------------------------ derived-weight caches
+    def invalidate_caches(self):
+        """Drop W2a / projection / BatchNorm-affine tensors derived from the parameters.  They are keyed on
+        (data_ptr, _version), which misses in-place writes through `param.data` (EMA copy_to / restore, utils/utils.py:353-392):
+        `sampling()` calls this on the model at the start of every call, and `.to()` / `load_state_dict` / `train()` do too."""
+        self._w2a_cache.clear()
+        self._proj_cache.clear()
+        self._param_cache.clear()
+        if self.batch_norm is not None:
+            self.batch_norm.invalidate_caches()
+
+    def _apply(self, fn, *a, **kw):
+        self._w2a_cache.clear(); self._proj_cache.clear(); self._param_cache.clear()
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self._w2a_cache.clear(); self._proj_cache.clear(); self._param_cache.clear()
+        return super()._load_from_state_dict(*a, **kw)
+
+    def train(self, mode=True):
+        self.invalidate_caches()
+        return super().train(mode)
 
     # ------------------------------------------------------------------ helpers
     def _fc(self, g):

@@ -60,8 +60,11 @@ def get_model(args, device, t_to_sigma, no_parallel=False, confidence_mode=False
         depthwise_convolution=args.depthwise_convolution if hasattr(args, "depthwise_convolution") else False)
     # The reference wraps the model in PyG DataParallel on CUDA (training only; sampling always uses
     # `.module`, finetune_train.py:177).  One process per GPU here: expose `.module` without a wrapper.
+    device = torch.device(device)
     if device.type == "cuda" and not no_parallel and not (has("dataset") and args.dataset == "torsional"):
-        model.module = model
+        # plain attribute, NOT a registered child: nn.Module.__setattr__ would make the model its own submodule and every
+        # recursive call (.to / .eval / .state_dict / .parameters) would never terminate
+        object.__setattr__(model, "module", model)
     model.to(device)
     return model
 
@@ -126,7 +129,14 @@ def crop_beyond(complex_graph, cutoff, all_atoms):
         ar.edge_index = ar_new
     for st in (rec, complex_graph["atom"] if all_atoms else None):
         if st is not None:
-            for stale in ("cb200_static", "ptr"):
+            for stale in ("cb200_static", "cb200_static_aa", "ptr"):
                 if stale in st:
                     delattr(st, stale)
+    # every graph kept a different subset of its receptor: the collate's bookkeeping no longer describes the batch
+    g = getattr(complex_graph, "_g", None)
+    if isinstance(g, dict):
+        if "_replicated_types" in g:
+            g["_replicated_types"] = [t for t in g["_replicated_types"] if t not in ("receptor", "atom")]
+        if "_slices" in g:
+            g["_slices_stale"] = True      # Batch.to_data_list re-derives slices / offsets from the batch vectors
     return complex_graph

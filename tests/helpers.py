@@ -104,3 +104,64 @@ def rmsd(a, b):
 def rel_err(a, b):
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     return ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+
+
+def blockwise_err(a, b, blocks=None):
+    """Worst element-wise error with every block judged on its OWN scale (a global max-norm ratio lets
+    small-magnitude blocks, e.g. the 1e / 0o channels, be off by far more than the bar and still pass):
+
+        max over blocks, over elements of   |a - b| / max(|b|, rms(b_block))
+
+    `blocks` = list of (start, stop) column ranges of the last dimension (one per irreps block); None = one block.
+    Elements below the block's RMS are judged against the RMS (an fp32 sum of O(rms) terms cannot be more accurate
+    than eps * rms in absolute terms, whatever its own magnitude)."""
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.numel() == 0:
+        return 0.0
+    if a.dim() == 1:
+        a, b = a.unsqueeze(1), b.unsqueeze(1)
+    blocks = blocks or [(0, a.shape[-1])]
+    worst = 0.0
+    for lo, hi in blocks:
+        bb, aa = b[..., lo:hi], a[..., lo:hi]
+        rms = bb.pow(2).mean().sqrt().clamp(min=1e-30)
+        worst = max(worst, ((aa - bb).abs() / torch.maximum(bb.abs(), rms)).max().item())
+    return worst
+
+
+def irreps_blocks(irreps: str):
+    """(start, stop) column range of every irreps block of an e3nn-style string such as '32x0e + 6x1o'."""
+    out, off = [], 0
+    for part in irreps.replace(" ", "").split("+"):
+        mul, ir = part.split("x")
+        d = int(mul) * (2 * int(ir[:-1]) + 1)
+        out.append((off, off + d))
+        off += d
+    return out
+
+
+class SlicedNoiseTape(NoiseTape):
+    """Noise for an oracle run over the FIRST `rows` graphs of a batch of `full_rows` graphs: every draw is generated
+    at the full batch's size (so the stream matches the product run on the full batch) and its first rows returned."""
+
+    def __init__(self, seed, rows, full_rows):
+        super().__init__(seed)
+        self.rows, self.full_rows = rows, full_rows
+
+    def __call__(self, mean=0, std=1, size=None, device=None, **kw):
+        size = tuple(size)
+        assert size[0] % self.rows == 0
+        per = size[0] // self.rows
+        z = super().__call__(mean, std, (per * self.full_rows,) + size[1:], device)
+        return z[: size[0]]
+
+
+@contextmanager
+def injected_sliced_noise(seed, rows, full_rows):
+    tape, orig = SlicedNoiseTape(seed, rows, full_rows), torch.normal
+    torch.normal = tape
+    try:
+        yield tape
+    finally:
+        torch.normal = orig

@@ -26,7 +26,12 @@ def test_partition_lpt_is_deterministic_and_balanced():
 def _fake_result(i, n_samples):
     n_atoms = 5 + 3 * i
     g = torch.Generator().manual_seed(100 + i)
-    return torch.randn(n_samples, n_atoms, 3, generator=g), (torch.randn(n_samples, generator=g) if i % 2 == 0 else None)
+    pose = torch.randn(n_samples, n_atoms, 3, generator=g)
+    if i % 4 == 0:
+        return pose, torch.randn(n_samples, generator=g)           # scalar confidence head: [S]
+    if i % 4 == 2:
+        return pose, torch.randn(n_samples, 3, generator=g)        # multi-class head (rmsd_classification_cutoff list): [S, k]
+    return pose, None
 
 
 def _worker(rank, world, port, n_complexes, q):
@@ -42,7 +47,8 @@ def _worker(rank, world, port, n_complexes, q):
             seen.append(i)
             return _fake_result(i, n)
 
-        poses, confs = cbdist.sample_complexes(complexes, 4, sample_fn, device=torch.device("cpu"))
+        # device=None: a rank that owns no complex (n_complexes=1) must still pick a device the backend accepts
+        poses, confs = cbdist.sample_complexes(complexes, 4, sample_fn, device=None)
         ok = True
         for i in range(n_complexes):
             p, c = _fake_result(i, 4)

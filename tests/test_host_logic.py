@@ -225,3 +225,77 @@ def test_collate_flags_replicated_node_types():
     assert "receptor" in flagged and "atom" in flagged and "ligand" not in flagged
     assert Batch.from_data_list([copy.deepcopy(a), copy.deepcopy(b)], device="cpu")._g["_replicated_types"] == []
     assert Batch.from_data_list(same)._g["_replicated_types"] == []      # the host collate does not compare
+
+
+def test_to_data_list_after_in_place_edit_rebuilds_slices():
+    """crop_beyond edits a batch in place; the collate's slices must not be trusted afterwards."""
+    import copy
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    gs = [make_complex(s, 20 + 5 * s, 6 + s, all_atoms=True, lm_dim=4) for s in range(3)]
+    b = Batch.from_data_list(copy.deepcopy(gs))
+    # drop the first two residues of graph 1 by hand (what crop_beyond does, on the host)
+    rec = b["receptor"]
+    keep = torch.ones(rec.pos.shape[0], dtype=torch.bool)
+    o1 = gs[0]["receptor"].num_nodes
+    keep[o1:o1 + 2] = False
+    remap = torch.cumsum(keep.long(), 0) - 1
+    rr, ar, atom, aa = b["receptor", "receptor"], b["atom", "receptor"], b["atom"], b["atom", "atom"]
+    ek = keep[rr.edge_index[0]] & keep[rr.edge_index[1]]
+    rr.edge_index = remap[rr.edge_index[:, ek]]
+    akeep = keep[ar.edge_index[1]]
+    amap = torch.cumsum(akeep.long(), 0) - 1
+    ar.edge_index = torch.stack([torch.arange(int(akeep.sum())), remap[ar.edge_index[1]][akeep]])
+    ek = akeep[aa.edge_index[0]] & akeep[aa.edge_index[1]]
+    aa.edge_index = amap[aa.edge_index[:, ek]]
+    atom.x, atom.pos, atom.batch = atom.x[akeep], atom.pos[akeep], atom.batch[akeep]
+    rec.x, rec.pos, rec.batch = rec.x[keep], rec.pos[keep], rec.batch[keep]
+    b._g["_slices_stale"] = True
+    out = b.to_data_list()
+    assert [d["receptor"].num_nodes for d in out] == [gs[0]["receptor"].num_nodes, gs[1]["receptor"].num_nodes - 2, gs[2]["receptor"].num_nodes]
+    assert torch.equal(out[0]["receptor", "receptor"].edge_index, gs[0]["receptor", "receptor"].edge_index)
+    assert torch.equal(out[2]["receptor", "receptor"].edge_index, gs[2]["receptor", "receptor"].edge_index)
+    assert torch.equal(out[2]["atom", "receptor"].edge_index, gs[2]["atom", "receptor"].edge_index)
+    assert torch.equal(out[2]["atom"].pos, gs[2]["atom"].pos)
+    assert int(out[1]["receptor", "receptor"].edge_index.max()) < out[1]["receptor"].num_nodes
+    assert torch.equal(out[1]["ligand"].pos, gs[1]["ligand"].pos)
+
+
+def test_derived_weight_caches_are_invalidated():
+    """EMA-style `param.data.copy_()` does not bump tensor versions; the folded tensors must still follow."""
+    from confidence_bootstrapping_b200.tensor_layers import TensorProductConvLayer
+    torch.manual_seed(0)
+    layer = TensorProductConvLayer("8x0e + 2x1o", "1x0e + 1x1o", "8x0e + 2x1o", 24, hidden_features=24, faster=True).eval()
+    w2a = layer._w2a(0).clone()
+    scale, shift = [t.clone() for t in layer.batch_norm.affine()]
+    W2 = layer.fc[3].weight
+    W2.data.copy_(W2.data * 2)                       # what ExponentialMovingAverage.copy_to does
+    layer.batch_norm.weight.data.copy_(layer.batch_norm.weight.data * 3)
+    assert torch.equal(layer._w2a(0), w2a)           # the version-keyed cache cannot see it ...
+    layer.invalidate_caches()                        # ... which is why sampling() refreshes per call
+    assert torch.allclose(layer._w2a(0)[:, :24], 2 * w2a[:, :24])
+    assert torch.allclose(layer.batch_norm.affine()[0], 3 * scale)
+    # .train()/.eval(), load_state_dict and .to() refresh as well
+    W2.data.copy_(W2.data * 0.5)
+    layer.train(False)
+    assert torch.allclose(layer._w2a(0)[:, :24], w2a[:, :24])
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    sd["fc.3.weight"] = sd["fc.3.weight"] * 4
+    layer._w2a(0)
+    layer.load_state_dict(sd)
+    assert torch.allclose(layer._w2a(0)[:, :24], 4 * w2a[:, :24])
+
+
+def test_sampling_scopes_eval_mode_and_restores_train_mode():
+    """finetune_train.py:177 samples with the score model in train mode; sampling() must not raise."""
+    import warnings
+    from confidence_bootstrapping_b200 import sampling as smp
+    net = torch.nn.Sequential(torch.nn.Linear(2, 2), torch.nn.Dropout(0.5)).train()
+    other = torch.nn.Linear(2, 2).eval()
+    smp._warned_train_mode = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with smp._inference_mode(net, other, None):
+            assert not net.training and not net[1].training and not other.training
+    assert net.training and net[1].training and not other.training
+    assert any("train mode" in str(x.message) for x in w)
