@@ -27,7 +27,7 @@ ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
 ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "2"))
 FOLD_E_POST = True            # fold W1e.e_post[graph] into the node projection on the host (tests switch it off to cover the kernel path)
 DEBUG_KEEP_WORKSPACE = None   # tests may set this to a list to inspect the K3 accumulators
-WORKSPACE_BYTES = 16 << 30  # cap on the K3 accumulator workspace (180 GB of HBM3e per GPU); larger layers run in node chunks
+WORKSPACE_BYTES = int(os.environ.get("CB200_WORKSPACE_MB", str(16 << 10))) << 20  # cap on the K3 accumulator workspace (180 GB of HBM3e per GPU); larger layers run in node chunks
 
 
 def FCBlock(in_dim, hidden_dim, out_dim, layers, dropout, activation="relu"):

@@ -57,11 +57,28 @@ def hyper_from_args(args, confidence_mode=False):
         in_lig_edge_features=4)
 
 
+def to_double(sd, batch):
+    """fp64 mode of the oracle: (state_dict, batch) with every floating tensor promoted to float64.  The neighbour
+    searches keep their fp32 predicate (oracle/cluster.py casts positions to fp32), so the edge sets are the fp32 ones and
+    only the arithmetic on them is carried out in double: the resulting outputs are the yardstick that tells fp32
+    rounding noise (oracle-fp32 vs oracle-fp64) from a real discrepancy (product vs oracle-fp64)."""
+    up = lambda v: v.double() if torch.is_tensor(v) and v.is_floating_point() else v
+    sd64 = {k: up(v) for k, v in sd.items()}
+    for st in batch._stores.values():
+        for k, v in list(st._d.items()):
+            st._d[k] = {kk: up(u) for kk, u in v.items()} if isinstance(v, dict) else up(v)
+    for k, v in list(batch._g.items()):
+        if not k.startswith("_"):
+            batch._g[k] = {kk: up(u) for kk, u in v.items()} if isinstance(v, dict) else up(v)
+    return sd64, batch
+
+
 def sinusoidal(t, dim, scale):
     """utils/diffusion_utils.py:99-110 applied to scale*t."""
     half = dim // 2
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
-    ang = (scale * t).float()[:, None] * freq[None, :]
+    dt = t.dtype if torch.is_tensor(t) and t.dtype == torch.float64 else torch.float32      # fp64 mode: see to_double()
+    freq = torch.exp(torch.arange(half, dtype=dt) * -(math.log(10000) / (half - 1)))
+    ang = (scale * t).to(dt)[:, None] * freq[None, :]
     return torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)
 
 
@@ -306,7 +323,7 @@ def _score_heads(sd, hp, data, lig_x, node_sigma, out_irreps, emb_t, tr_sigma, r
     B, ct = data.num_graphs, data.complex_t
     # translation / rotation head (:394-420)
     cidx = torch.stack([lig.batch, torch.arange(len(lig.batch))])
-    center = torch.zeros((B, 3)).index_add_(0, lig.batch, lig.pos) / torch.bincount(lig.batch, minlength=B).unsqueeze(1)
+    center = torch.zeros((B, 3), dtype=lig.pos.dtype).index_add_(0, lig.batch, lig.pos) / torch.bincount(lig.batch, minlength=B).unsqueeze(1)
     cv = lig.pos[cidx[1]] - center[cidx[0]]
     ca = torch.cat([_smear(sd, "center_distance_expansion", cv.norm(dim=-1)), node_sigma[cidx[1]]], 1)
     ca = _fc(sd, "center_edge_embedding", ca)
@@ -347,7 +364,7 @@ def _score_heads(sd, hp, data, lig_x, node_sigma, out_irreps, emb_t, tr_sigma, r
     tor = F.linear(torch.tanh(F.linear(tor, sd["tor_final_layer.0.weight"])), sd["tor_final_layer.3.weight"]).squeeze(1)
     if hp.scale_by_sigma:
         edge_sigma = tor_sigma[lig.batch][ll.edge_index[0]][lig.edge_mask]
-        tor = tor * torch.sqrt(torch.tensor(torus_score_norm(edge_sigma.cpu().numpy())).float())
+        tor = tor * torch.sqrt(torch.tensor(torus_score_norm(edge_sigma.cpu().numpy())).to(tor.dtype))
     return tr, rot, tor, None
 
 

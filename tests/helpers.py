@@ -165,3 +165,25 @@ def injected_sliced_noise(seed, rows, full_rows):
         yield tape
     finally:
         torch.normal = orig
+
+
+def load_1a0q(all_atoms=True, lm_dim=1280, lm_seed=0):
+    """The reference's shipped complex data/1a0q (BASELINE.json config 1) from the committed fixture
+    (oracle/make_1a0q_fixture.py).  Residue LM embeddings are seeded N(0,1) (the ESM2 cache is a preprocessing product)."""
+    d = torch.load(os.path.join(GOLDEN, "1a0q.pt"), weights_only=False)
+    g = unpack_graph(d)
+    rec = g["receptor"]
+    aa = rec.x.float()
+    if lm_dim:
+        lm = torch.from_numpy(np.random.default_rng(lm_seed).normal(size=(aa.shape[0], lm_dim)).astype(np.float32))
+        aa = torch.cat([aa, lm], 1)
+    rec.x = aa
+    g["atom"].x = g["atom"].x.float()
+    g["ligand"].x = g["ligand"].x.long()
+    for et in g.edge_types:
+        g[et].edge_index = g[et].edge_index.long()
+    if not all_atoms:
+        for key in [k for k in list(g._stores) if k == "atom" or (isinstance(k, tuple) and "atom" in (k[0], k[2]))]:
+            del g._stores[key]
+    g.name = "1a0q"
+    return g

@@ -237,18 +237,27 @@ def test_config5_slice_all_atom_score_model_vs_oracle():
     torch.manual_seed(5)
     dl = [copy.deepcopy(g) for _ in range(2)]
     randomize_position(dl, False, False, 6.0)       # within reach of the 5 A ligand-atom graph for some atoms
+    o_t2s = partial(osamp.t_to_sigma, args=args)
     for t in (0.5, 1.0):
         cpu = Batch.from_data_list(copy.deepcopy(dl))
         osamp.set_time(cpu, t, t, t, 2, all_atoms=True)
+        cpu64 = Batch.from_data_list(copy.deepcopy(dl))
+        osamp.set_time(cpu64, t, t, t, 2, all_atoms=True)
+        sd64, cpu64 = om.to_double(sd, cpu64)
         gpu = Batch.from_data_list(copy.deepcopy(dl), device="cuda")
         set_time(gpu, None, t, t, t, 2, True, False, dev)
         with torch.no_grad():
-            want = om.aa_forward(sd, hp, cpu, partial(osamp.t_to_sigma, args=args), so3.score_norm, torus.score_norm)
+            want = om.aa_forward(sd, hp, cpu, o_t2s, so3.score_norm, torus.score_norm)
+            want64 = om.aa_forward(sd64, hp, cpu64, o_t2s, so3.score_norm, torus.score_norm)      # same edges, fp64 arithmetic
             got = model(gpu)
-        for a, b, name in zip(got[:3], want[:3], ("tr", "rot", "tor")):
+        for a, b, b64, name in zip(got[:3], want[:3], want64[:3], ("tr", "rot", "tor")):
             assert a.shape == b.shape
-            err = blockwise_err(a, b)
-            assert err < FORWARD_TOL, (name, t, err)
+            # The heads of a random-init lmax-2 model are differences of O(1) terms: the fp32 oracle itself sits 3e-5 .. 8e-5
+            # (element-wise) from the fp64 evaluation of the same graph.  Bar: FORWARD_TOL against the fp64 yardstick, or
+            # twice the fp32 oracle's own distance to it where that is larger (i.e. not worse than fp32 rounding noise).
+            noise = blockwise_err(b, b64)
+            err = blockwise_err(a, b64)
+            assert err < max(FORWARD_TOL, 2.0 * noise), (name, t, err, noise)
 
 
 def test_tor_bond_conv_layer_vs_oracle():
@@ -366,3 +375,34 @@ class _null:
 
     def __exit__(self, *a):
         return False
+
+
+def test_config1_1a0q_sampling_and_confidence_vs_oracle():
+    """BASELINE config 1: the reference's shipped complex data/1a0q (416 residues, 23 heavy ligand atoms, 11 torsions) with the
+    shipped score / confidence hyper-parameters, 10 samples x 20 steps + crop_beyond(20 A) + confidence scoring, against the CPU
+    oracle with the same noise: poses within 1e-3 A RMSD, confidences within 1e-4 (BASELINE.json north_star)."""
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule
+    from confidence_bootstrapping_b200.sampling import randomize_position, sampling
+    from helpers import load_1a0q
+    m = _models(seed=12, confidence=True)
+    args, cargs = m["args"], m["cargs"]
+    g = Batch.from_data_list([load_1a0q()])
+    np.random.seed(11)
+    torch.manual_seed(11)
+    S, steps = 10, 20
+    dl = [copy.deepcopy(g) for _ in range(S)]
+    randomize_position(dl, False, False, args.tr_sigma_max)
+    dl_cpu, fl, fl_cpu = copy.deepcopy(dl), copy.deepcopy(dl), copy.deepcopy(dl)
+    sched = get_t_schedule("expbeta", steps, 1, 1)
+    with injected_noise(seed=31):
+        out, conf = sampling(data_list=dl, model=m["model"], inference_steps=steps, tr_schedule=sched, rot_schedule=sched,
+                             tor_schedule=sched, device=torch.device("cuda"), t_to_sigma=m["t2s"], model_args=args, batch_size=S,
+                             confidence_model=m["cmodel"], filtering_data_list=fl, filtering_model_args=cargs)
+    with injected_noise(seed=31):
+        ref, rconf = osamp.sampling(dl_cpu, m["oracle_fwd"], steps, sched, sched, sched, m["o_t2s"], args, batch_size=S,
+                                    confidence_forward=m["oracle_conf"], filtering_data_list=fl_cpu,
+                                    filtering_model_args=cargs, crop_fn=osamp.crop_beyond)
+    worst = max(rmsd(a["ligand"].pos, b["ligand"].pos) for a, b in zip(out, ref))
+    assert worst < 1e-3, worst
+    assert torch.allclose(conf.cpu(), rconf, atol=1e-4), (conf.cpu() - rconf).abs().max()

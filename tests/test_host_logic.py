@@ -299,3 +299,33 @@ def test_sampling_scopes_eval_mode_and_restores_train_mode():
             assert not net.training and not net[1].training and not other.training
     assert net.training and net[1].training and not other.training
     assert any("train mode" in str(x.message) for x in w)
+
+
+def test_1a0q_fixture_known_answers():
+    """BASELINE config 1 input: the parsed data/1a0q complex has the sizes SURVEY.md section 8a derived from the shipped files
+    (416 residues, 3183 receptor heavy atoms, 23 ligand heavy atoms, 46 directed bond edges, 11 rotatable bonds, 9962
+    rec-rec edges at r = 15 A / 24 neighbours, 242 ligand radius-5 edges with max degree 15)."""
+    from helpers import load_1a0q
+    from oracle import cluster
+    g = load_1a0q()
+    assert g["receptor"].num_nodes == 416 and g["receptor"].x.shape == (416, 1281)
+    assert g["atom"].num_nodes == 3183 and g["atom"].x.shape[1] == 4
+    assert g["ligand"].num_nodes == 23 and g["ligand"].x.shape == (23, 16)
+    ll = g["ligand", "ligand"]
+    assert ll.edge_index.shape == (2, 46) and ll.edge_attr.shape == (46, 4)
+    assert int(g["ligand"].edge_mask.sum()) == 11 and g["ligand"].mask_rotate.shape == (11, 23)
+    assert g["receptor", "receptor"].edge_index.shape == (2, 9962)
+    assert torch.bincount(g["receptor", "receptor"].edge_index[1]).max() <= 24       # <= 24 neighbours per centre
+    assert g["atom", "receptor"].edge_index.shape == (2, 3183)
+    # feature indices stay inside the embedding vocabularies (process_mols.py:95-123)
+    from confidence_bootstrapping_b200.synthetic import LIG_FEATURE_DIMS, REC_ATOM_FEATURE_DIMS
+    assert all(int(g["ligand"].x[:, i].max()) < d for i, d in enumerate(LIG_FEATURE_DIMS[0]))
+    assert all(int(g["atom"].x[:, i].max()) < d for i, d in enumerate(REC_ATOM_FEATURE_DIMS[0]))
+    assert float(g["receptor"].pos.mean(0).abs().max()) < 1e-3                        # centred on the C-alpha centroid
+    b = torch.zeros(23, dtype=torch.long)
+    rad = cluster.radius_graph(g["ligand"].pos, 5.0, b)
+    assert rad.shape[1] == 242 and int(torch.bincount(rad[1]).max()) == 15
+    # torsion.py:81-82 orientation of the rotation masks
+    ei = ll.edge_index.T[g["ligand"].edge_mask]
+    for k, (u, v) in enumerate(ei.tolist()):
+        assert not g["ligand"].mask_rotate[k, u] and g["ligand"].mask_rotate[k, v]
