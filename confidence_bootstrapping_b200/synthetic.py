@@ -33,6 +33,32 @@ def _knn_radius_edges(pos: np.ndarray, cutoff: float, max_neighbors: int) -> np.
     return np.asarray([dst, src], dtype=np.int64)
 
 
+def _knn_radius_edges_fast(pos: np.ndarray, cutoff: float, max_neighbors: int) -> np.ndarray:
+    """Same edge list as `_knn_radius_edges` (verified element for element in tests/test_host_logic.py) from one batched
+    KD-tree query instead of the dense N x N distance matrix + Python loop: 1000-residue / 8000-atom receptors in
+    milliseconds instead of ten seconds."""
+    from scipy.spatial import cKDTree
+    n = len(pos)
+    k = min(n, max_neighbors + 2)                       # self + (max_neighbors + 1) others
+    dist, idx = cKDTree(pos).query(pos, k=k)
+    dist, idx = dist.reshape(n, k), idx.reshape(n, k)
+    src, dst = [], []
+    for i in range(n):
+        others = idx[i][idx[i] != i][: k - 1]
+        # exact distances as the dense path computes them (the tree's own may differ in the last bit at the cutoff)
+        d = np.linalg.norm(pos[i][None, :] - pos[others], axis=-1) if len(others) else np.zeros(0)
+        inside = others[d < cutoff]
+        if len(inside) > max_neighbors:
+            nb = [int(j) for j in others[np.argsort(d, kind="stable")][:max_neighbors]]
+        elif len(inside) == 0:
+            nb = [int(others[int(np.argmin(d))])] if len(others) else []
+        else:
+            nb = sorted(int(j) for j in inside)
+        src += [i] * len(nb)
+        dst += nb
+    return np.asarray([dst, src], dtype=np.int64)
+
+
 def rotatable_bond_masks(n_atoms: int, edges: np.ndarray):
     """`get_transformation_mask` (utils/torsion.py:15-45) without networkx/PyG.
 
@@ -147,7 +173,7 @@ def make_complex(seed: int, n_res: int, n_lig: int, all_atoms: bool = True, lm_d
     g["receptor"].pos = torch.from_numpy(ca.astype(np.float32))
     g["receptor"].side_chain_vecs = torch.from_numpy(rng.normal(size=(n_res, 11)).astype(np.float32))
     g["receptor", "rec_contact", "receptor"].edge_index = torch.from_numpy(
-        _knn_radius_edges(ca, receptor_radius, c_alpha_max_neighbors))
+        _knn_radius_edges_fast(ca, receptor_radius, c_alpha_max_neighbors))
     g.original_center = torch.from_numpy(center.astype(np.float32))
 
     if all_atoms:
@@ -165,7 +191,7 @@ def make_complex(seed: int, n_res: int, n_lig: int, all_atoms: bool = True, lm_d
         g["atom"].x = torch.from_numpy(ax.astype(np.float32))
         g["atom"].pos = torch.from_numpy(apos.astype(np.float32))
         g["atom", "atom_contact", "atom"].edge_index = torch.from_numpy(
-            _knn_radius_edges(apos, atom_radius, atom_max_neighbors))
+            _knn_radius_edges_fast(apos, atom_radius, atom_max_neighbors))
         g["atom", "atom_rec_contact", "receptor"].edge_index = torch.from_numpy(
             np.stack([np.arange(n_atom), np.asarray(aidx)]).astype(np.int64))
 

@@ -329,3 +329,10 @@ def test_1a0q_fixture_known_answers():
     ei = ll.edge_index.T[g["ligand"].edge_mask]
     for k, (u, v) in enumerate(ei.tolist()):
         assert not g["ligand"].mask_rotate[k, u] and g["ligand"].mask_rotate[k, v]
+
+
+def test_fast_knn_radius_edges_equal_the_dense_loop():
+    from confidence_bootstrapping_b200.synthetic import _knn_radius_edges, _knn_radius_edges_fast
+    for seed, n, cutoff, mx in [(0, 300, 15.0, 24), (1, 120, 15.0, 24), (2, 900, 5.0, 8), (3, 5, 15.0, 24), (4, 60, 3.0, 8), (5, 2, 1.0, 8)]:
+        pos = np.random.default_rng(seed).normal(size=(n, 3)) * (n ** (1 / 3)) * 3
+        assert np.array_equal(_knn_radius_edges(pos, cutoff, mx), _knn_radius_edges_fast(pos, cutoff, mx)), (seed, n)
