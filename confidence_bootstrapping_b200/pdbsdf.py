@@ -159,6 +159,10 @@ def receptor_graph(g: HeteroData, residues, all_atoms=True, receptor_radius=15.0
         feats.append(np.random.default_rng(lm_seed).normal(size=(len(residues), lm_dim)).astype(np.float32))
     g["receptor"].x = torch.from_numpy(np.concatenate(feats, 1))
     g["receptor"].pos = torch.from_numpy(ca.astype(np.float32))
+    # side_chain_vecs = [chi angles / 360 (5) | N - CA | C - CA] (process_mols.py:450-452); only crop_beyond carries it along
+    # (utils/utils.py:414), no model reads it; the chi angles need the side-chain topology tables and are left at zero
+    rel = lambda nm: np.asarray([next((a[2] for a in atoms if a[0] == nm), c) for (_, atoms), c in zip(residues, ca)]) - ca
+    g["receptor"].side_chain_vecs = torch.from_numpy(np.concatenate([np.zeros((len(ca), 5)), rel("N"), rel("C")], 1).astype(np.float32))
     # rows [neighbour, centre]: what the dataset path builds (pdbbind.py:396 -> process_mols.py:415,448-481)
     g["receptor", "rec_contact", "receptor"].edge_index = torch.from_numpy(_knn_radius_edges(ca, receptor_radius, c_alpha_max_neighbors))
     if all_atoms:
