@@ -57,8 +57,13 @@ class TpConvArgs(C.Structure):
         ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p), ("residual", C.c_void_p),
         ("d_res", C.c_int32), ("ld_res", C.c_int32), ("out", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_floats", C.c_int64), ("node_begin", C.c_int32), ("node_end", C.c_int32),
-        ("accum_mode", C.c_int32), ("pad_", C.c_int32),
+        ("accum_mode", C.c_int32), ("flags", C.c_int32),
+        ("pre_sum", C.c_void_p), ("pre_deg", C.c_void_p), ("pre_n0", C.c_int32), ("pre_n1", C.c_int32),
+        ("pre_period", C.c_int32), ("pad_", C.c_int32),
     ]
+
+
+CB_TP_RAW_SUM = 1
 
 
 class SdeStepArgs(C.Structure):

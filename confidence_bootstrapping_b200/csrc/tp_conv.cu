@@ -1354,9 +1354,18 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
         const int n = i / d_out, o = i - n * d_out;
         const int node = t0 + n;
         if (node < a.node_end && chan_owner[o] == split) {
-            float v = outacc[i] / (float)max(deg_tot[n], 1);
-            if (a.bn_scale) v = fmaf(v, a.bn_scale[o], a.bn_shift[o]);
-            if (a.residual && o < a.d_res) v += a.residual[(size_t)node * a.ld_res + o];
+            float v = outacc[i];
+            if (!(a.flags & CB_TP_RAW_SUM)) {
+                int deg = deg_tot[n];
+                if (a.pre_sum != nullptr && node >= a.pre_n0 && node < a.pre_n1) {   // sample-invariant part computed once (cb200.h)
+                    const int k = (node - a.pre_n0) % a.pre_period;
+                    v += __ldg(a.pre_sum + (size_t)k * d_out + o);
+                    deg += __ldg(a.pre_deg + k);
+                }
+                v = v / (float)max(deg, 1);
+                if (a.bn_scale) v = fmaf(v, a.bn_scale[o], a.bn_shift[o]);
+                if (a.residual && o < a.d_res) v += a.residual[(size_t)node * a.ld_res + o];
+            }
             a.out[(size_t)node * d_out + o] = v;
         }
     }
@@ -1410,6 +1419,9 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
                  a->H, a->ne);
     CB_CHECK_ARG(a->n_rows > 0 && a->n_runs > 0 && a->d_out > 0 && a->d_in > 0 && a->S > 0, "cb_tp_conv_forward: bad sizes");
     CB_CHECK_ARG((a->bn_scale == nullptr) == (a->bn_shift == nullptr), "cb_tp_conv_forward: bn_scale/bn_shift must come together");
+    CB_CHECK_ARG((a->pre_sum == nullptr) == (a->pre_deg == nullptr), "cb_tp_conv_forward: pre_sum/pre_deg must come together");
+    CB_CHECK_ARG(a->pre_sum == nullptr || (a->pre_period > 0 && 0 <= a->pre_n0 && a->pre_n0 <= a->pre_n1 && a->pre_n1 <= a->n_out),
+                 "cb_tp_conv_forward: pre_sum range [%d,%d) period %d outside [0,%d)", a->pre_n0, a->pre_n1, a->pre_period, a->n_out);
     CB_CHECK_ARG(0 <= a->node_begin && a->node_end <= a->n_out, "cb_tp_conv_forward: node range [%d,%d) outside [0,%d)",
                  a->node_begin, a->node_end, a->n_out);
     for (int s = 0; s < a->n_segs; ++s) {

@@ -90,6 +90,9 @@ def _i32(t):
     return t.to(torch.int32).contiguous()
 
 
+SHARE_REPLICATED_REC_MESSAGES = True   # tests switch it off to compare with the general path
+
+
 class _Static:
     """Per-Batch cache of everything that does not depend on the ligand pose or the diffusion time."""
 
@@ -293,6 +296,9 @@ class TensorProductScoreModel(nn.Module):
                 seg = Segment(e_first, rec_e_attr[:e0], rec_sh[:e0], 0, 0, n0)
                 x = layer.run(x.contiguous(), [seg], n0, ns, (0, ns), (ns, ns), (2 * ns, ns), residual=x.contiguous())
             x = x.repeat(B, 1)
+            # sample-invariant rec->rec messages of the first conv layer are computed on this first copy (forward())
+            st.rec_first = SimpleNamespace(n0=n0, e0=e0, edges=e_first,
+                                           deg=(st.rec_edges.rowptr[1:n0 + 1] - st.rec_edges.rowptr[:n0]).contiguous())
         else:
             x = self.rec_node_embedding(st.rec_x)
             for layer in self.rec_emb_layers:
@@ -367,13 +373,28 @@ class TensorProductScoreModel(nn.Module):
         g = (0, 1, 2, 3) if self.differentiate_convolutions else (0, 0, 0, 0)
         n_layers = len(self.conv_layers)
         gates = self._dead_output_gates(st, rl, n_layers)
+        # In the FIRST conv layer the receptor rows of the B copies of one complex are still identical (same receptor, same
+        # t), so the rec->rec slot -- 40 % of the layer's edges -- is aggregated and transformed once for the first copy and
+        # shared (cb_tp_conv_args.pre_sum).  Needs the collate's "replicated receptor" flag and one diffusion time for the
+        # whole batch (what sampling() feeds: utils/sampling.py:110); anything else takes the general path.
+        host_t = getattr(data, "complex_t_host", None) if hasattr(data, "complex_t_host") else None
+        share_rec = (SHARE_REPLICATED_REC_MESSAGES and getattr(st, "rec_first", None) is not None and host_t is not None
+                     and n_layers > 1)
         for l, layer in enumerate(self.conv_layers):
             if l < n_layers - 1:
                 gate = gates.get(l)
-                segs = lig_segments(g[0], NL) + [
-                    Segment(lr, lr_attr, lr_sh, g[1], 0, NL, col_off=NL),
+                cross = [Segment(lr, lr_attr, lr_sh, g[1], 0, NL, col_off=NL)]
+                rec_in = Segment(rl, rl_attr, rl_sh, g[3], NL, NL + NR, col_off=0)
+                if l == 0 and share_rec:
+                    f = st.rec_first
+                    first = Segment(f.edges, st.rec_e_attr[:f.e0], st.rec_sh[:f.e0], g[2], 0, f.n0, col_off=0, e_post=rec_sigma_emb)
+                    pre_sum = layer.run(x[NL:NL + f.n0], [first], f.n0, ns, raw_sum=True, **cols)
+                    segs = lig_segments(g[0], NL) + cross + [rec_in]
+                    x = layer.run(x, segs, NL + NR, ns, agg_graph=node_graph, residual=x, pre=(pre_sum, f.deg, NL, NL + NR), **cols)
+                    continue
+                segs = lig_segments(g[0], NL) + cross + [
                     Segment(st.rec_edges, st.rec_e_attr, st.rec_sh, g[2], NL, NL + NR, col_off=NL, e_post=rec_sigma_emb, gate=gate),
-                    Segment(rl, rl_attr, rl_sh, g[3], NL, NL + NR, col_off=0)]
+                    rec_in]
                 x = layer.run(x, segs, NL + NR, ns, agg_graph=node_graph, residual=x, **cols)
             else:
                 # last layer only updates the ligand rows (the reference normalises the others but never reads them)

@@ -236,13 +236,16 @@ class TensorProductConvLayer(nn.Module):
 
     # ------------------------------------------------------------------ fused path
     def run(self, x, segments: List[Segment], n_out, ns, e_cols, agg_cols=None, nbr_cols=None,
-            agg_scalars=None, agg_graph=None, residual=None):
+            agg_scalars=None, agg_graph=None, residual=None, raw_sum=False, pre=None):
         """x [N_in, d_in]; returns [n_out, d_out].
 
         e_cols / agg_cols / nbr_cols: (offset, width) of the edge-embedding, aggregation-side and
         neighbour-side scalar blocks inside the first Linear's input (tensor_layers.py:201-202 applied
         to the concatenations built at score_model.py:290-291,314,367-368,397,439-440).
-        agg_scalars: [n_out, ns] table for the aggregation side (defaults to x[:, :ns])."""
+        agg_scalars: [n_out, ns] table for the aggregation side (defaults to x[:, :ns]).
+        raw_sum: return the un-normalised sums over incoming edges (no mean / BatchNorm / residual).
+        pre: (sum [period, d_out], deg int32 [period], n0, n1) -- a sample-invariant contribution from an earlier
+        raw_sum call, added to aggregation nodes [n0, n1) with period `period` before the mean (cb200.h)."""
         self._check_mode()
         dev = x.device
         P = self.program
@@ -321,10 +324,18 @@ class TensorProductConvLayer(nn.Module):
             sg.W1e, sg.ldw1 = _lib.f32(W1, "W1") + 4 * e_cols[0], W1.shape[1]
             sg.b1, sg.W2a = _lib.f32(b1, "b1"), _lib.f32(W2a, "W2a")
             sg.n0, sg.n1, sg.col_off, sg.slot = s.n0, s.n1, s.col_off, slot_ids[k]
-        if self.batch_norm is not None:
+        if raw_sum:
+            a.flags = _lib.CB_TP_RAW_SUM
+            assert residual is None and pre is None
+        elif self.batch_norm is not None:
             scale, shift = self.batch_norm.affine()
             a.bn_scale, a.bn_shift = scale.data_ptr(), shift.data_ptr()
             keep += [scale, shift]
+        if pre is not None:
+            p_sum, p_deg, p_n0, p_n1 = pre
+            assert p_sum.shape[1] == P.d_out and p_deg.numel() == p_sum.shape[0] and (p_n1 - p_n0) % p_sum.shape[0] == 0
+            a.pre_sum, a.pre_deg = _lib.f32(p_sum, "pre_sum"), _lib.i32(p_deg, "pre_deg")
+            a.pre_n0, a.pre_n1, a.pre_period = p_n0, p_n1, p_sum.shape[0]
         if residual is not None:
             a.residual, a.d_res, a.ld_res = _lib.f32(residual, "residual"), min(residual.shape[1], P.d_out), residual.shape[1]
         a.out = out.data_ptr()

@@ -178,8 +178,17 @@ typedef struct {
     float* workspace; int64_t workspace_floats;
     int32_t node_begin, node_end;
     int32_t accum_mode;     /* accumulate kernel: 1 = fp32 FFMA register tiles, 2 = tcgen05 3xTF32 with TMEM accumulator */
-    int32_t pad_;
+    int32_t flags;          /* CB_TP_RAW_SUM: write the un-normalised sums (no mean, BatchNorm, residual) */
+    /* Sample-invariant contribution computed by an earlier CB_TP_RAW_SUM call: aggregation node i in
+     * [pre_n0, pre_n1) additionally receives pre_sum[(i - pre_n0) % pre_period][:] before the mean and counts
+     * pre_deg[(i - pre_n0) % pre_period] more incoming edges.  Use: the S copies of one receptor in a sampling batch
+     * have identical rec->rec messages in the first conv layer (same receptor, same t: models/score_model.py:298-320,
+     * 365-370), so they are aggregated and transformed once for one copy and shared by all S.  NULL = none.        */
+    const float* pre_sum;   /* [pre_period, d_out]                                               */
+    const int32_t* pre_deg; /* [pre_period]                                                      */
+    int32_t pre_n0, pre_n1, pre_period, pad_;
 } cb_tp_conv_args;
+#define CB_TP_RAW_SUM 1
 /* number of (node, slot) accumulators the call will use (host arithmetic only) */
 int64_t cb_tp_conv_items(const cb_tp_conv_args* a);
 int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream);

@@ -353,3 +353,55 @@ def test_replicated_receptor_embedding_is_tiled():
             outs.append(model(batch))
     for a, b in zip(outs[0][:3], outs[1][:3]):
         assert rel_err(a, b) < 1e-6
+
+
+@pytest.mark.gpu
+def test_shared_first_layer_receptor_messages_match_the_general_path():
+    """Conv layer 0: the rec->rec slot of the S copies of one receptor is aggregated + transformed once for the first copy
+    and added through cb_tp_conv_args.pre_sum.  Same scores as the general path up to the order of the fp32 additions
+    (the shared sum joins the per-sample sums after the transform instead of inside its register accumulators), and a
+    16x smaller layer-0 item count."""
+    import confidence_bootstrapping_b200.score_model as sm
+    from confidence_bootstrapping_b200 import _lib
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import set_time
+    from confidence_bootstrapping_b200.sampling import randomize_position
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    from helpers import blockwise_err
+    args = score_model_args()
+    model, t2s, _ = _build(args, seed=7)
+    g = Batch.from_data_list([make_complex(43, 300, 22, all_atoms=False)])
+    np.random.seed(3); torch.manual_seed(3)
+    dl = [copy.deepcopy(g) for _ in range(16)]
+    randomize_position(dl, False, False, args.tr_sigma_max)
+    outs, items = [], []
+
+    class Count:
+        def __init__(self):
+            self.n = []
+
+        def __call__(self, a):
+            import contextlib
+            self.n.append(_lib.tp_conv_items(a))
+            return contextlib.nullcontext()
+
+    for share in (True, False):
+        sm.SHARE_REPLICATED_REC_MESSAGES = share
+        try:
+            for t in (1.0, 0.2):
+                batch = Batch.from_data_list(copy.deepcopy(dl), device="cuda")
+                set_time(batch, None, t, t, t, batch.num_graphs, False, False, torch.device("cuda"))
+                c = Count()
+                _lib.tp_conv_hook = c
+                with torch.no_grad():
+                    outs.append(model(batch))
+                _lib.tp_conv_hook = None
+                items.append(sum(c.n))
+        finally:
+            sm.SHARE_REPLICATED_REC_MESSAGES = True
+            _lib.tp_conv_hook = None
+    for k in range(2):
+        for a, b in zip(outs[k][:3], outs[k + 2][:3]):
+            assert blockwise_err(a, b) < 2e-6
+        assert items[k] < items[k + 2]
