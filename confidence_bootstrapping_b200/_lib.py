@@ -74,6 +74,7 @@ class SdeStepArgs(C.Structure):
         ("z_tr", C.c_void_p), ("z_rot", C.c_void_p), ("z_tor", C.c_void_p),
         ("c_tr_score", C.c_float), ("c_tr_noise", C.c_float), ("c_rot_score", C.c_float),
         ("c_rot_noise", C.c_float), ("c_tor_score", C.c_float), ("c_tor_noise", C.c_float),
+        ("coeffs_dev", C.c_void_p),
     ]
 
 

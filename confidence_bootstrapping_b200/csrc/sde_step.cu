@@ -121,7 +121,13 @@ sde_step_kernel(cb_sde_step_args a) {
     float* flx = rig + 3 * N;             // [N][3] conformer being twisted
     float* gp = a.pos + (size_t)g * 3 * N;
 
-    // perturbations
+    // perturbations.  Coefficients by value, or read from device memory (a step loop captured in a CUDA graph keeps its
+    // launch parameters: the per-step scalars then live in a device array the host refreshes between replays)
+    if (a.coeffs_dev != nullptr) {
+        a.c_tr_score = __ldg(a.coeffs_dev + 0); a.c_tr_noise = __ldg(a.coeffs_dev + 1);
+        a.c_rot_score = __ldg(a.coeffs_dev + 2); a.c_rot_noise = __ldg(a.coeffs_dev + 3);
+        a.c_tor_score = __ldg(a.coeffs_dev + 4); a.c_tor_noise = __ldg(a.coeffs_dev + 5);
+    }
     float tr[3], rot[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

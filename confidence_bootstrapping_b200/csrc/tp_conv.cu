@@ -1114,6 +1114,36 @@ __device__ __forceinline__ void row_fma2(const float* const (&ap)[NT], const flo
     }
 }
 
+// Wide runs (mul > 8: the 0e output block, two thirds of the transform's FMAs): a thread owns 2 nodes x MT outputs and
+// visits its K chunks kc, kc + KSTRIDE_W, ...; even / odd K columns accumulate in the two halves of a register pair
+// (fma.rn.f32x2), so the 2 x MT x 2 partial sums fill the same 64 registers the 4 x MT scalar tile used while the inner
+// loop issues 82 instead of 276 instructions per 256 MACs.
+constexpr int NTW = 2;
+constexpr int KSTRIDE_W = 2 * WPC;
+template <int MT>
+__device__ __forceinline__ void row_fma2_wide(const float* const (&ap)[NTW], const float* __restrict__ Wb, int HA, int a4, int kc, int nvalid,
+                                              float (&acc)[NT][MTMAX]) {
+    static_assert(NTW * MT * 2 <= NT * MTMAX, "pair accumulators must fit the register tile");
+#pragma unroll 1
+    for (int k = kc; k < a4; k += KSTRIDE_W) {
+        float4 av[NTW];
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) av[j] = *reinterpret_cast<const float4*>(ap[j] + 4 * k);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const float4 w = *reinterpret_cast<const float4*>(Wb + (m < nvalid ? m : 0) * HA + 4 * k);
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) {
+                constexpr int dummy = 0; (void)dummy;
+                float& lo = acc[(j * 2 * MT + 2 * m) / MTMAX][(j * 2 * MT + 2 * m) % MTMAX];
+                float& hi = acc[(j * 2 * MT + 2 * m + 1) / MTMAX][(j * 2 * MT + 2 * m + 1) % MTMAX];
+                fma2(lo, hi, av[j].x, av[j].y, w.x, w.y);
+                fma2(lo, hi, av[j].z, av[j].w, w.z, w.w);
+            }
+        }
+    }
+}
+
 struct ConsumerCtx {
     float* sm; const int* items; const int* n_items; uint32_t full_bar, empty_bar;   // barriers: shared-space addresses of [STAGES]
     int stage, a_stage, zero, n_active, HA, a4, nl, kc, lane;
@@ -1123,13 +1153,17 @@ struct ConsumerCtx {
 // all row groups of one run (over every active slot) for one consumer thread
 template <int MT>
 __device__ __forceinline__ void run_groups(const ConsumerCtx& c, int& G, float (&acc)[NT][MTMAX]) {
+    constexpr bool WIDE = 2 * MT > MTMAX;       // mul > 8 runs: 2 nodes per thread, packed FMAs (row_fma2_wide)
+    constexpr int NN = WIDE ? NTW : NT;
+    const int nl = WIDE ? (c.lane & 15) : c.nl, nstep = WIDE ? 16 : 8;
+    const int kc = WIDE ? (c.kc >> 2) * 2 + (c.lane >> 4) : c.kc;     // c.kc = 4 * warp-in-combo + (lane >> 3)
 #pragma unroll 1
     for (int k = 0; k < c.n_active; ++k) {
         const int n_act = c.n_items[k];
-        int a_off[NT];      // offset of the thread's nodes inside the A stage, or -1: nodes without edges read zeros
+        int a_off[NN];      // offset of the thread's nodes inside the A stage, or -1: nodes without edges read zeros
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            const int rank = c.items[k * NB + c.nl + 8 * j];
+        for (int j = 0; j < NN; ++j) {
+            const int rank = c.items[k * NB + nl + nstep * j];
             a_off[j] = rank >= 0 ? (c.rs * n_act + rank) * c.HA : -1;
         }
 #pragma unroll 1
@@ -1138,11 +1172,11 @@ __device__ __forceinline__ void run_groups(const ConsumerCtx& c, int& G, float (
             const float* Ab = c.sm + s * c.stage;
             tc::mbar_wait_addr(c.full_bar + 8u * s, (G / STAGES) & 1);
             if (c.mine && rg + c.rs < c.row_end) {
-                const float* ap[NT];
+                const float* ap[NN];
 #pragma unroll
-                for (int j = 0; j < NT; ++j) ap[j] = a_off[j] >= 0 ? Ab + a_off[j] : c.sm + c.zero;
-                if constexpr (2 * MT <= MTMAX) row_fma2<MT>(ap, Ab + c.a_stage + c.w_off, c.HA, c.a4, c.kc, c.nvalid, acc);
-                else row_fma<MT>(ap, Ab + c.a_stage + c.w_off, c.HA, c.a4, c.kc, c.nvalid, acc);
+                for (int j = 0; j < NN; ++j) ap[j] = a_off[j] >= 0 ? Ab + a_off[j] : c.sm + c.zero;
+                if constexpr (WIDE) row_fma2_wide<MT>(ap, Ab + c.a_stage + c.w_off, c.HA, c.a4, kc, c.nvalid, acc);
+                else row_fma2<MT>(ap, Ab + c.a_stage + c.w_off, c.HA, c.a4, c.kc, c.nvalid, acc);
             }
             __syncwarp();
             if (c.lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c.empty_bar + 8u * s) : "memory");
@@ -1321,19 +1355,37 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
             }
             // ---- end of the run: reduce the partial sums in a fixed order and add into the output channels
             asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");   // the previous run's reducers are done with `part`
+            if (2 * run.mt <= MTMAX) {      // uniform.  Thread tiles of <= 8 outputs: 4 nodes, even / odd K columns in two slots per output (row_fma2)
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int m = 0; m < MTMAX / 2; ++m)
+                        if (m < run.mt) {
+                            float v = acc[j][2 * m] + acc[j][2 * m + 1];
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            v += __shfl_xor_sync(0xffffffffu, v, 16);
+                            if (lane < 8) part[((warp * 8 + nl) * NT + j) * MTMAX + m] = v;
+                        }
+            } else {                        // wide tiles: 2 nodes (lane & 15, + 16) x run.mt outputs, pairs at 2 * (j * mt + m)
+#pragma unroll
+                for (int j = 0; j < NTW; ++j)
+#pragma unroll
+                    for (int m = 0; m < MTMAX; ++m)
+                        if (m < run.mt) {
+                            // flat pair index 2 * (j * mt + m): the run's mt is one of 12 / 16 (dispatch below)
+                            const int f12 = 2 * (j * 12 + m), f16 = 2 * (j * 16 + m);
+                            const float v12 = m < 12 ? acc[(f12 / MTMAX) % NT][f12 % MTMAX] + acc[((f12 + 1) / MTMAX) % NT][(f12 + 1) % MTMAX] : 0.0f;
+                            const float v16 = acc[f16 / MTMAX][f16 % MTMAX] + acc[(f16 + 1) / MTMAX][(f16 + 1) % MTMAX];
+                            float v = run.mt == 12 ? v12 : v16;
+                            v += __shfl_xor_sync(0xffffffffu, v, 16);
+                            const int n = (lane & 15) + 16 * j;
+                            if (lane < 16) part[((warp * 8 + (n & 7)) * NT + (n >> 3)) * MTMAX + m] = v;
+                        }
+            }
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
-                for (int m = 0; m < MTMAX; ++m) {
-                    if (m < run.mt) {       // uniform
-                        // thread tiles of <= 8 outputs keep even / odd K columns in two slots per output (row_fma2)
-                        float v = 2 * run.mt <= MTMAX ? acc[j][(2 * m) % MTMAX] + acc[j][(2 * m + 1) % MTMAX] : acc[j][m];
-                        v += __shfl_xor_sync(0xffffffffu, v, 8);
-                        v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if (lane < 8) part[((warp * 8 + nl) * NT + j) * MTMAX + m] = v;
-                    }
-                    acc[j][m] = 0.0f;
-                }
+                for (int m = 0; m < MTMAX; ++m) acc[j][m] = 0.0f;
             asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
 #pragma unroll 1
             for (int i = tid; i < NB * run.mul; i += CT) {

@@ -117,7 +117,8 @@ class LigandTopology:
 
 def sde_step(pos, topo: LigandTopology, tr_score, rot_score, tor_score, coeffs, z_tr=None, z_rot=None, z_tor=None):
     """In-place pose update: perturbation = c_score * score + c_noise * z, then rigid move, bond
-    rotations, Kabsch re-alignment.  coeffs = (c_tr_s, c_tr_n, c_rot_s, c_rot_n, c_tor_s, c_tor_n)."""
+    rotations, Kabsch re-alignment.  coeffs = (c_tr_s, c_tr_n, c_rot_s, c_rot_n, c_tor_s, c_tor_n) as host
+    floats, or a float32 CUDA tensor with those six values (read by the kernel: CUDA-graph replays)."""
     a = _lib.SdeStepArgs()
     a.pos = _lib.f32(pos, "pos")
     a.B, a.N, a.R = topo.B, topo.N, topo.R
@@ -132,7 +133,11 @@ def sde_step(pos, topo: LigandTopology, tr_score, rot_score, tor_score, coeffs, 
     a.z_tr = _lib.f32(z_tr, "z_tr", allow_none=True)
     a.z_rot = _lib.f32(z_rot, "z_rot", allow_none=True)
     a.z_tor = _lib.f32(z_tor, "z_tor", allow_none=True) if use_tor else None
-    (a.c_tr_score, a.c_tr_noise, a.c_rot_score, a.c_rot_noise, a.c_tor_score, a.c_tor_noise) = [float(c) for c in coeffs]
+    if torch.is_tensor(coeffs):
+        assert coeffs.numel() == 6
+        a.coeffs_dev = _lib.f32(coeffs, "coeffs")
+    else:
+        (a.c_tr_score, a.c_tr_noise, a.c_rot_score, a.c_rot_noise, a.c_tor_score, a.c_tor_noise) = [float(c) for c in coeffs]
     _lib.sde_step(a)
     return pos
 

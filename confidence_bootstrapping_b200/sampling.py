@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import contextlib
 import copy
+import os
 import warnings
 
 import numpy as np
@@ -170,13 +171,55 @@ def _inference_mode(*models):
                 m.train(True)
 
 
+USE_CUDA_GRAPH = os.environ.get("CB200_CUDA_GRAPH", "1") != "0"
+_graph_warned = False
+
+
+def _step_scalars(t_idx, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_to_sigma, model_args, g_const, no_random, ode,
+                  no_final_step_noise, temp_sampling, temp_psi, temp_sigma_data, no_torsion):
+    """Host arithmetic of one reverse step (sampling.py:94-99,119-167): times, and per component the coefficients of
+    perturbation = c_score * score + c_noise * z.  Returns (t(3), coeffs(6), noisy(3 bools))."""
+    last = t_idx == inference_steps - 1
+    ts = (tr_schedule[t_idx], rot_schedule[t_idx], tor_schedule[t_idx])
+    dts = [s[t_idx] - s[t_idx + 1] if not last else s[t_idx] for s in (tr_schedule, rot_schedule, tor_schedule)]
+    sigmas = t_to_sigma(*ts)
+    noiseless = no_random or (no_final_step_noise and last)
+    coeffs, noisy = [], []
+    for k, name in enumerate(("tr", "rot", "tor")):
+        if k == 2 and no_torsion:
+            coeffs += [0.0, 0.0]
+            noisy.append(False)
+            continue
+        g, dt, temp, psi, sig = sigmas[k] * g_const[name], dts[k], temp_sampling[k], temp_psi[k], sigmas[k]
+        smax, smin = getattr(model_args, f"{name}_sigma_max"), getattr(model_args, f"{name}_sigma_min")
+        if ode:
+            c_s, c_n, z = 0.5 * g ** 2 * dt, 0.0, False
+        else:
+            z = not noiseless
+            c_s, c_n = g ** 2 * dt, g * np.sqrt(dt)
+            if temp != 1.0:
+                sigma_data = np.exp(temp_sigma_data * np.log(smax) + (1 - temp_sigma_data) * np.log(smin))
+                lam = (sigma_data + sig) / (sigma_data + sig / temp)
+                c_s, c_n = g ** 2 * dt * (lam + temp * psi / 2), g * np.sqrt(dt * (1 + psi))
+        coeffs += [float(c_s), float(c_n)]
+        noisy.append(z)
+    return ts, coeffs, noisy
+
+
 def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma,
                       model_args, mask_rotate, noise_rows=None, no_random=False, ode=False, t_schedule=None,
                       no_final_step_noise=False, temp_sampling=(1.0, 1.0, 1.0), temp_psi=(0.0, 0.0, 0.0),
-                      temp_sigma_data=0.5):
+                      temp_sigma_data=0.5, use_graph=None):
     """The hot loop of sampling.py:93-223 on a batch that already lives on the device: `inference_steps` x
     (score-model forward, K4 pose update).  Returns the final [B*N, 3] positions (also left in
-    batch['ligand'].pos).  No host synchronisation inside."""
+    batch['ligand'].pos).  No host synchronisation inside.
+
+    The first step runs eagerly (it builds the per-batch static cache and the derived-weight caches); the second is
+    captured into a CUDA graph -- buffers are sized by host-known upper bounds, edge counts stay on the device, and the
+    step's scalars (t per component, the six perturbation coefficients, the so3 / torus score norms) are read from a
+    small device array -- and every later step is one graph replay after refreshing that array and the noise buffers.
+    ~200 launches / 8 ms of host enqueue per step become one launch; the arithmetic is the eager path's, bit for bit."""
+    from . import _lib, so3, torus
     b = batch.num_graphs
     N = noise_rows if noise_rows is not None else b
     batch_size = N
@@ -189,54 +232,96 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
         temp_sampling = [temp_sampling] * 3
     if not _is_iterable(temp_psi):
         temp_psi = [temp_psi] * 3
+    if hasattr(model_args, "crop_beyond") and model_args.crop_beyond is not None:
+        raise NotImplementedError("per-step crop_beyond for the score model is not in the shipped score YAML")
     topo = LigandTopology(batch, mask_rotate, device)
     pos = batch["ligand"].pos.float().contiguous()
     batch["ligand"].pos = pos
-    for t_idx in range(inference_steps):
-        t_tr, t_rot, t_tor = tr_schedule[t_idx], rot_schedule[t_idx], tor_schedule[t_idx]
-        last = t_idx == inference_steps - 1
-        dt_tr = tr_schedule[t_idx] - tr_schedule[t_idx + 1] if not last else tr_schedule[t_idx]
-        dt_rot = rot_schedule[t_idx] - rot_schedule[t_idx + 1] if not last else rot_schedule[t_idx]
-        dt_tor = tor_schedule[t_idx] - tor_schedule[t_idx + 1] if not last else tor_schedule[t_idx]
-        tr_sigma, rot_sigma, tor_sigma = t_to_sigma(t_tr, t_rot, t_tor)
-        if hasattr(model_args, "crop_beyond") and model_args.crop_beyond is not None:
-            raise NotImplementedError("per-step crop_beyond for the score model is not in the shipped score YAML")
-        set_time(batch, t_schedule[t_idx] if t_schedule is not None else None, t_tr, t_rot, t_tor, b, all_atoms,
-                 asyncronous_noise_schedule, device)
-        tr_score, rot_score, tor_score = model(batch)[:3]
+    nb = min(batch_size, N)
+    if use_graph is None:
+        use_graph = USE_CUDA_GRAPH
+    use_graph = bool(use_graph) and pos.is_cuda and inference_steps >= 4 and _lib.tp_conv_hook is None
+    scal = lambda k: _step_scalars(k, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_to_sigma, model_args, g_const,
+                                   no_random, ode, no_final_step_noise, temp_sampling, temp_psi, temp_sigma_data, no_torsion)
 
-        # sampling.py:119-167 -- g = sigma * sqrt(2 ln(smax/smin)); perturbation is linear in (score, z)
-        tr_g, rot_g, tor_g = tr_sigma * g_const["tr"], rot_sigma * g_const["rot"], tor_sigma * g_const["tor"]
-        noiseless = no_random or (no_final_step_noise and last)
-        nb = min(batch_size, N)
-        coeffs, zs = [], []
-        for k, (g, dt, temp, psi, sig, smax, smin, shape) in enumerate((
-                (tr_g, dt_tr, temp_sampling[0], temp_psi[0], tr_sigma, model_args.tr_sigma_max, model_args.tr_sigma_min, (nb, 3)),
-                (rot_g, dt_rot, temp_sampling[1], temp_psi[1], rot_sigma, model_args.rot_sigma_max, model_args.rot_sigma_min, (nb, 3)),
-                (tor_g, dt_tor, temp_sampling[2], temp_psi[2], tor_sigma, model_args.tor_sigma_max, model_args.tor_sigma_min, None))):
-            if k == 2 and no_torsion:
-                coeffs += [0.0, 0.0]
+    def draw(noisy, tor_shape):
+        """torch.normal in the reference's order (sampling.py:126-141): tr, rot, tor."""
+        zs = []
+        for k, shape in enumerate(((nb, 3), (nb, 3), tor_shape)):
+            if not noisy[k]:
                 zs.append(None)
                 continue
-            if k == 2:
-                shape = tuple(tor_score.shape)
-            if ode:
-                c_s, c_n, z = 0.5 * g ** 2 * dt, 0.0, None
-            else:
-                z = None if noiseless else torch.normal(mean=0, std=1, size=shape, device=device)
-                c_s, c_n = g ** 2 * dt, g * np.sqrt(dt)
-                if temp != 1.0:
-                    sigma_data = np.exp(temp_sigma_data * np.log(smax) + (1 - temp_sigma_data) * np.log(smin))
-                    lam = (sigma_data + sig) / (sigma_data + sig / temp)
-                    c_s, c_n = g ** 2 * dt * (lam + temp * psi / 2), g * np.sqrt(dt * (1 + psi))
-            if z is not None and k < 2 and z.shape[0] != b:
+            z = torch.normal(mean=0, std=1, size=shape, device=device)
+            if k < 2 and z.shape[0] != b:
                 raise RuntimeError(f"noise batch {z.shape[0]} != graphs in batch {b} (sampling.py:126-131: "
                                    "batch_size must divide the number of samples)")
-            coeffs += [float(c_s), float(c_n)]
-            zs.append(z.float().contiguous() if z is not None else None)
-        sde_step(pos, topo, tr_score, rot_score, None if no_torsion else tor_score, coeffs, zs[0], zs[1], zs[2])
+            zs.append(z.float().contiguous())
+        return zs
 
+    graph, vals, z_static, tor_shape, graph_launches = None, None, None, None, 0
+    for t_idx in range(inference_steps):
+        (t_tr, t_rot, t_tor), coeffs, noisy = scal(t_idx)
+        if graph is None:
+            # ---- eager step (always the first one; every one when graphs are off)
+            set_time(batch, t_schedule[t_idx] if t_schedule is not None else None, t_tr, t_rot, t_tor, b, all_atoms,
+                     asyncronous_noise_schedule, device)
+            if hasattr(batch, "cb200_step"):
+                batch.cb200_step = None
+            tr_score, rot_score, tor_score = model(batch)[:3]
+            tor_shape = tuple(tor_score.shape)
+            zs = draw(noisy, tor_shape)
+            sde_step(pos, topo, tr_score, rot_score, None if no_torsion else tor_score, coeffs, zs[0], zs[1], zs[2])
+            if use_graph and t_idx == 0:
+                try:
+                    graph, vals, z_static, graph_launches = _capture_step(batch, model, pos, topo, b, nb, tor_shape, no_torsion,
+                                                                          scal(1)[2], device)
+                except Exception as e:          # capture is an optimisation: the eager loop is always correct
+                    global _graph_warned
+                    if not _graph_warned:
+                        warnings.warn(f"cb200: CUDA-graph capture of the reverse-diffusion step failed ({type(e).__name__}: {e}); "
+                                      "continuing with eager launches")
+                        _graph_warned = True
+                    graph, use_graph = None, False
+            continue
+        # ---- graph replay: refresh the step's scalars and noise, then one launch
+        sig = t_to_sigma(t_tr, t_rot, t_tor)
+        so3_norm = float(so3.score_norm(torch.full((1,), float(sig[1]), dtype=torch.float32))[0])
+        torus_norm = float(torch.tensor(torus.score_norm(np.asarray([sig[2]], dtype=np.float32))).float()[0]) if not no_torsion else 1.0
+        host = torch.tensor([t_tr, t_rot, t_tor, *coeffs, so3_norm, torus_norm], dtype=torch.float32)
+        vals.copy_(host, non_blocking=False)
+        zs = draw(noisy, tor_shape)
+        for zb, z in zip(z_static, zs):
+            if (zb is None) != (z is None):
+                raise RuntimeError("cb200: noise pattern changed between graph replays")
+            if zb is not None:
+                zb.copy_(z)
+        graph.replay()
+        _lib.launch_count += graph_launches
+    if graph is not None:
+        batch.cb200_step = None
+        set_time(batch, None, tr_schedule[inference_steps - 1], rot_schedule[inference_steps - 1], tor_schedule[inference_steps - 1], b,
+                 all_atoms, asyncronous_noise_schedule, device)
     return pos
+
+
+def _capture_step(batch, model, pos, topo, b, nb, tor_shape, no_torsion, noisy, device):
+    """One reverse step (score-model forward + K4) captured into a CUDA graph whose per-step inputs live in static device
+    buffers: vals = [t_tr, t_rot, t_tor, c_tr_s, c_tr_n, c_rot_s, c_rot_n, c_tor_s, c_tor_n, so3_norm, torus_norm]."""
+    from . import _lib
+    vals = torch.zeros(11, dtype=torch.float32, device=device)
+    vals[:3] = 0.5          # a valid time while capturing (nothing executes, but shapes / code paths are those of a real step)
+    z_static = [torch.zeros((nb, 3), device=device) if noisy[0] else None, torch.zeros((nb, 3), device=device) if noisy[1] else None,
+                torch.zeros(tor_shape, device=device) if noisy[2] else None]
+    batch.complex_t = {"tr": vals[0:1].expand(b), "rot": vals[1:2].expand(b), "tor": vals[2:3].expand(b)}
+    batch.complex_t_host = None
+    batch.cb200_step = {"so3_norm": vals[9:10], "torus_norm": vals[10:11]}
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    l0 = _lib.launch_count
+    with torch.cuda.graph(graph):
+        tr_score, rot_score, tor_score = model(batch)[:3]
+        sde_step(pos, topo, tr_score, rot_score, None if no_torsion else tor_score, vals[3:9], z_static[0], z_static[1], z_static[2])
+    return graph, vals, z_static, _lib.launch_count - l0
 
 
 def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,

@@ -378,8 +378,9 @@ class TensorProductScoreModel(nn.Module):
         # shared (cb_tp_conv_args.pre_sum).  Needs the collate's "replicated receptor" flag and one diffusion time for the
         # whole batch (what sampling() feeds: utils/sampling.py:110); anything else takes the general path.
         host_t = getattr(data, "complex_t_host", None) if hasattr(data, "complex_t_host") else None
-        share_rec = (SHARE_REPLICATED_REC_MESSAGES and getattr(st, "rec_first", None) is not None and host_t is not None
-                     and n_layers > 1)
+        step = getattr(data, "cb200_step", None) if hasattr(data, "cb200_step") else None      # device-resident step scalars (CUDA graph)
+        share_rec = (SHARE_REPLICATED_REC_MESSAGES and getattr(st, "rec_first", None) is not None
+                     and (host_t is not None or step is not None) and n_layers > 1)
         for l, layer in enumerate(self.conv_layers):
             if l < n_layers - 1:
                 gate = gates.get(l)
@@ -451,9 +452,11 @@ class TensorProductScoreModel(nn.Module):
         rot_norm = torch.linalg.vector_norm(rot_pred, dim=1).unsqueeze(1)
         rot_pred = rot_pred / rot_norm * self.rot_final_layer(torch.cat([rot_norm, sigma_emb], dim=1))
         host_t = getattr(data, "complex_t_host", None) if hasattr(data, "complex_t_host") else None
+        step = getattr(data, "cb200_step", None) if hasattr(data, "cb200_step") else None
         if self.scale_by_sigma:
             tr_pred = tr_pred / tr_sigma.unsqueeze(1)
-            rot_pred = rot_pred * so3.score_norm_device(rot_sigma, host_t, self.t_to_sigma, dev).unsqueeze(1)
+            so3_norm = step["so3_norm"].expand(B) if step is not None else so3.score_norm_device(rot_sigma, host_t, self.t_to_sigma, dev)
+            rot_pred = rot_pred * so3_norm.unsqueeze(1)
         if self.no_torsion or st.n_tor == 0:
             return tr_pred, rot_pred, torch.empty(0, device=dev), None
 
@@ -479,8 +482,11 @@ class TensorProductScoreModel(nn.Module):
         tor_pred = self.tor_bond_conv.run(lig_x, seg, n_tor, ns, (0, ns), (2 * ns, ns), (ns, ns), agg_scalars=bond_attr_sum)
         tor_pred = self.tor_final_layer(tor_pred).squeeze(1)
         if self.scale_by_sigma:
-            edge_sigma = tor_sigma[st.tor_batch.long()]
-            tor_pred = tor_pred * torch.sqrt(torus.score_norm_device(edge_sigma, host_t, self.t_to_sigma, st.tor_batch, dev))
+            if step is not None:
+                tor_pred = tor_pred * torch.sqrt(step["torus_norm"])
+            else:
+                edge_sigma = tor_sigma[st.tor_batch.long()]
+                tor_pred = tor_pred * torch.sqrt(torus.score_norm_device(edge_sigma, host_t, self.t_to_sigma, st.tor_batch, dev))
         return tr_pred, rot_pred, tor_pred, None
 
     def _confidence_head(self, lig_x, st):

@@ -209,6 +209,8 @@ typedef struct {
     const float* tr_score; const float* rot_score; const float* tor_score; /* [B,3],[B,3],[B*R] */
     const float* z_tr; const float* z_rot; const float* z_tor;            /* noise or NULL (0) */
     float c_tr_score, c_tr_noise, c_rot_score, c_rot_noise, c_tor_score, c_tor_noise;
+    const float* coeffs_dev;    /* optional [6] device copy of the six coefficients above (same order); when non-NULL it
+                                   overrides them, so a CUDA-graph replay can change the step's scalars          */
 } cb_sde_step_args;
 int cb_sde_step(const cb_sde_step_args* a, void* stream);
 
