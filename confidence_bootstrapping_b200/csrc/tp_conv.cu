@@ -407,16 +407,17 @@ struct Layout {
     int dxp, npad, mtiles, sbow;
 };
 
-__host__ __device__ inline Layout make_layout(int n_rows, int n_terms, int ne, int d_in, int S, int H) {
+__host__ __device__ inline Layout make_layout(int n_rows, int n_terms, int ne, int d_in, int S, int H, bool transposed = false) {
     Layout L;
     auto al = [](int v, int a) { return (v + a - 1) / a * a; };
     L.sbow = (ne / 4) * LBO;     // stride between 8-row groups of the [.., ne] operand tiles of the hidden-layer MMA
     L.dxp = d_in + (d_in & 1);   // even: rows are filled with 8-byte cp.async
-    L.npad = al(H + 1, 16);
+    L.npad = transposed ? 128 : al(H + 1, 16);   // transposed: H~ is the M = 128 operand (rows >= H stay zero)
     L.mtiles = (n_rows + 127) / 128;
     int o = 0;
-    L.fhi = o;   o += L.mtiles * 16 * SBO;
-    L.flo = o;   o += L.mtiles * 16 * SBO;
+    const int f_groups = transposed ? (n_rows + 15) / 16 * 2 : L.mtiles * 16;   // 8-row groups of the F^T tile (transposed: N = rows padded to 16)
+    L.fhi = o;   o += f_groups * SBO;
+    L.flo = o;   o += f_groups * SBO;
     L.hhi = o;   o += (L.npad / 8) * SBO;
     L.hlo = o;   o += (L.npad / 8) * SBO;
     L.ehi = o;   o += (KC / 8) * L.sbow;
@@ -462,8 +463,9 @@ struct FRowCtx {
 // F^T tile row of one thread: F[r][e] = sum_t coef_t * x[col e][xi_t] * sh_e[si_t] for the chunk's edges, hi/lo split,
 // four consecutive edges per 16-byte core-matrix row.  NT = register-resident terms evaluated (warp-uniform).
 template <int NT>
-__device__ __forceinline__ void f_row(const FRowCtx& c, const int (&t_xi)[MAXT], const int (&t_si)[MAXT], const float (&t_cf)[MAXT]) {
+__device__ __forceinline__ float f_row(const FRowCtx& c, const int (&t_xi)[MAXT], const int (&t_si)[MAXT], const float (&t_cf)[MAXT]) {
     const int dx4 = 4 * c.dxp, s4 = 4 * c.S;
+    float total = 0.0f;          // sum_e f_e[r] over the chunk (bias term of the second Linear in the transposed kernel)
     const float* xe = c.xs;      // first edge of the current 4-edge group
     const float* se = c.shs;
 #pragma unroll 1
@@ -496,7 +498,9 @@ __device__ __forceinline__ void f_row(const FRowCtx& c, const int (&t_xi)[MAXT],
         split_tf32_trunc(v[3], hi.w, lo.w);
         *reinterpret_cast<float4*>(c.Fhi + c.rbase + e4 * LBO) = hi;   // 4 consecutive edges = one 16-byte core-matrix row
         *reinterpret_cast<float4*>(c.Flo + c.rbase + e4 * LBO) = lo;
+        total += (v[0] + v[1]) + (v[2] + v[3]);
     }
+    return total;
 }
 
 #ifdef CB_PHASE_TIMING
@@ -506,11 +510,20 @@ __device__ unsigned long long cb_dbg_phase[2][12];
 #define PH_MARK(k) do { } while (0)
 #endif
 
+// TR = false: D[f-row][h~ column] in MT x NP TMEM columns, read back through a shared-memory transpose (any layer shape).
+// TR = true : the accumulator is kept TRANSPOSED, D[h~ unit (128 lanes)][f-row (<= 240 columns)] = H~ . F^T -- one MMA per
+//             k-step and product instead of one per 128-row tile, 23 % fewer operand bytes read from shared memory, and a
+//             tcgen05.ld now returns 32 f-rows of ONE hidden unit per lane, so 32 lanes hold 128 contiguous workspace bytes
+//             of a row: the finished tile goes TMEM -> registers -> global with no shared-memory transpose (which was 19 %
+//             of the kernel's shared-memory traffic and 18 % of its stall samples, profiles/r1/k3_ncu_summary.txt).  The
+//             constant-1 row of H~ is dropped; column H of the workspace (sum_e f_e) is summed by the f-row threads.
+//             Needs n_rows <= 240 (TMEM: 240 + 16 columns) -- every layer of the score model.
+template <bool TR>
 __global__ void __launch_bounds__(THREADS, 2)
 tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int H = a.H, ne = a.ne, S = a.S, d_in = a.d_in, n_rows = a.n_rows;
-    const Layout L = make_layout(n_rows, a.n_terms, ne, d_in, S, H);
+    const Layout L = make_layout(n_rows, a.n_terms, ne, d_in, S, H, TR);
     const int dxp = L.dxp, NP = L.npad, MT = L.mtiles, HA = H + PADC, SBOW = L.sbow;
     unsigned char* Fhi = smraw + L.fhi;
     unsigned char* Flo = smraw + L.flo;
@@ -564,9 +577,11 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int NRP = (n_rows + 15) & ~15;       // transposed: accumulator columns (f-rows padded to the MMA's N granularity)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((TR ? NRP : NP) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc_h = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t tmem_h = tmem_base + (uint32_t)(MT * NP);   // [128 hidden lanes] x [KC edge columns] pre-activations
+    const uint32_t tmem_h = tmem_base + (uint32_t)(TR ? NRP : MT * NP);   // [128 hidden lanes] x [KC edge columns] pre-activations
+    float fsum = 0.0f;                         // transposed: sum_e f_e[tid] of the open item
     uint32_t commits = 0, waited = 0;   // block-uniform bookkeeping of the MMA barrier phases
     uint32_t h_phase = 0;
     int staged_slot = -1;
@@ -810,12 +825,14 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         const int nq = 2 * ((n + 7) >> 3);   // 4-edge groups covered by the MMA k-steps of this chunk
         if (tid < n_rows) {
             const FRowCtx fc{xs, shs, terms_s, Fhi, Flo, dxp, S, n, nq, tb0, te0, (tid >> 3) * SBO + (tid & 7) * 16};
+            float part;
             switch (nt_warp) {      // warp-uniform: most f-rows have a single term
-                case 1: f_row<1>(fc, t_xi, t_si, t_cf); break;
-                case 2: f_row<2>(fc, t_xi, t_si, t_cf); break;
-                case 3: f_row<3>(fc, t_xi, t_si, t_cf); break;
-                default: f_row<MAXT>(fc, t_xi, t_si, t_cf); break;
+                case 1: part = f_row<1>(fc, t_xi, t_si, t_cf); break;
+                case 2: part = f_row<2>(fc, t_xi, t_si, t_cf); break;
+                case 3: part = f_row<3>(fc, t_xi, t_si, t_cf); break;
+                default: part = f_row<MAXT>(fc, t_xi, t_si, t_cf); break;
             }
+            fsum = cur.first ? part : fsum + part;
         }
 #pragma unroll 1
         for (int r = tid + THREADS; r < n_rows; r += THREADS) {   // rows beyond the first 256 (lmax-2 layers)
@@ -862,7 +879,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (qq < NP) {
+                if (TR ? qq < H : qq < NP) {      // transposed: rows >= H keep the zeros written at kernel start
                     float h[8];
                     if (qq < H) {
                         const float hb = hbase[qq];
@@ -896,7 +913,23 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         __syncthreads();
         PH_MARK(11);
         // ---- one thread issues the MMAs of this chunk and commits them to the barrier
-        if (tid == 0) {
+        if (TR && tid == 0) {
+            // D[h~ unit][f-row] += H~ . F^T : A = H~ tile (M = 128 rows), B = F^T tile (N = NRP rows), one MMA per product
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc0 = cur.first ? 0u : 1u;
+            mma_tf32(tmem_base, d_hhi, d_fhi, idesc, acc0);
+            mma_tf32(tmem_base, d_hhi, d_flo, idesc, 1u);
+            mma_tf32(tmem_base, d_hlo, d_fhi, idesc, 1u);
+            if (ksteps > 1) {
+                const uint64_t ks = (uint64_t)((2 * LBO) >> 4);
+                mma_tf32(tmem_base, d_hhi + ks, d_fhi + ks, idesc, 1u);
+                mma_tf32(tmem_base, d_hhi + ks, d_flo + ks, idesc, 1u);
+                mma_tf32(tmem_base, d_hlo + ks, d_fhi + ks, idesc, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
+                         : "memory");
+        }
+        if (!TR && tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
@@ -928,6 +961,42 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             const int row_stride = ws_stride;
             float* Aout = a.workspace + ws_off;
             const int lg = warp & 3;                 // TMEM lane group this warp may access
+            if constexpr (TR) {
+                // lane = hidden unit j = 32 lg + lane, columns = f-rows: a warp-wide store of one column is 128 contiguous
+                // bytes of workspace row r.  The two warps of a lane group split the columns.
+                const int j = lg * 32 + lane;
+                if (lg * 32 < H) {                   // warp-uniform: lane groups beyond the hidden width hold nothing
+                    const int c_half = ((NRP / 2) + 15) & ~15;
+                    const int c_lo = (warp >> 2) ? c_half : 0, c_hi = (warp >> 2) ? NRP : c_half;
+                    float* dst = Aout + j;
+#pragma unroll 1
+                    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                            : "r"(taddr));
+                        const bool second = c0 + 16 < c_hi;
+                        if (second)
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                                : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                : "r"(taddr + 16u));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (j < H) {
+                            const int nr = min(second ? 32 : 16, n_rows - c0);      // f-rows of this batch that exist
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nr) dst[(size_t)(c0 + i) * row_stride] = __uint_as_float(v[i]);
+                        }
+                    }
+                }
+                // column H: sum_e f_e[r] (bias of the second Linear), then the three zero pad columns the transform multiplies by 0
+                if (tid < n_rows) *reinterpret_cast<float4*>(Aout + (size_t)tid * row_stride + H) = make_float4(fsum, 0.f, 0.f, 0.f);
+            } else {
             constexpr int STG_LD = 36;               // floats per staged row: 144-byte stride keeps float4 accesses conflict-free
             float* stg = reinterpret_cast<float*>(smraw + L.fhi) + warp * 32 * STG_LD;
 #pragma unroll 1
@@ -969,6 +1038,7 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     }
                     __syncwarp();
                 }
+            }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();   // TMEM tile fully read before the next item's first MMA overwrites it
@@ -1501,17 +1571,21 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
                      "cb_tp_conv_forward: workspace too small (%lld floats for %lld accumulators)",
                      (long long)a->workspace_floats, (long long)ws_items);
         int rc;
-        if (a->accum_mode == 2) {
+        if (a->accum_mode == 2 || a->accum_mode == 3) {
             CB_CHECK_ARG(a->d_in % 2 == 0, "cb_tp_conv_forward: tcgen05 accumulate needs an even node-feature width (d_in=%d)", a->d_in);
             CB_CHECK_ARG(R <= 384 && ((R + 127) / 128) * ((H + 1 + 15) / 16 * 16) + tc::KC <= tc::TMEM_COLS,
                          "cb_tp_conv_forward: tcgen05 accumulate supports rows<=384 and tiles within 256 TMEM columns (rows=%d H=%d)", R, H);
             CB_CHECK_ARG(a->ne % 8 == 0 && H <= 120, "cb_tp_conv_forward: tcgen05 accumulate needs ne %% 8 == 0 and H <= 120 (ne=%d H=%d)", a->ne, H);
-            const tc::Layout L = tc::make_layout(R, a->n_terms, a->ne, a->d_in, a->S, H);
+            // transposed accumulator (no shared-memory epilogue) whenever the f-rows fit 240 TMEM columns and the hidden width
+            // is a multiple of 32 (a lane group is either full or empty)
+            const bool transposed = a->accum_mode == 3 && R <= 240 && H % 32 == 0 && H <= 128;
+            const tc::Layout L = tc::make_layout(R, a->n_terms, a->ne, a->d_in, a->S, H, transposed);
             // at least 80 KB so that never more than 2 CTAs (2 x 256 TMEM columns) share an SM
             const size_t smem = (size_t)(L.total > 80 * 1024 ? L.total : 80 * 1024);
             // <= 112 KB: two CTAs per SM; wider edge embeddings (generic layer call) run one CTA per SM
             CB_CHECK_ARG(smem <= 220 * 1024, "cb_tp_conv_forward: tcgen05 accumulate needs %zu B of shared memory", smem);
-            cudaError_t e = cudaFuncSetAttribute(tc::tp_accumulate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            auto kern = transposed ? tc::tp_accumulate_tc_kernel<true> : tc::tp_accumulate_tc_kernel<false>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) {
                 cb_set_error("cb_tp_conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
                 return CB_ERR_CUDA;
@@ -1519,7 +1593,7 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
             const int per_sm = smem <= 112 * 1024 ? 2 : 1;
             const int blocks = (int)((items + tc::ITEM_BLOCK - 1) / tc::ITEM_BLOCK);
             const int grid = blocks < CB_NUM_SMS * per_sm ? blocks : CB_NUM_SMS * per_sm;
-            tc::tp_accumulate_tc_kernel<<<grid, tc::THREADS, smem, st>>>(*a, (int)items);
+            kern<<<grid, tc::THREADS, smem, st>>>(*a, (int)items);
             CB_CHECK_LAUNCH("cb_tp_conv_forward(accumulate, tcgen05)");
             rc = CB_OK;
         } else

@@ -173,6 +173,24 @@ def _inference_mode(*models):
 
 USE_CUDA_GRAPH = os.environ.get("CB200_CUDA_GRAPH", "1") != "0"
 _graph_warned = False
+_graph_pools = {}      # device index -> memory-pool handle shared by every step graph captured on that device
+
+
+def _graph_pool(device):
+    """One private memory pool per device for all step graphs: a graph's intermediates (K3 workspaces are GBs) are carved
+    from it during capture and return to it when the graph is dropped at the end of the sampling call, so the next call's
+    capture re-uses them instead of paying cudaMalloc / cudaFree of several GB per call (measured: +290 ms per call)."""
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _graph_pools:
+        # the allocator drops a pool when the last graph captured into it dies: a tiny keeper graph pins it for the process
+        pool = torch.cuda.graph_pool_handle()
+        keeper = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(keeper, pool=pool):
+            anchor = torch.zeros(8, device=torch.device("cuda", idx))
+        _graph_pools[idx] = (pool, keeper, anchor)
+    return _graph_pools[idx][0]
 
 
 def _step_scalars(t_idx, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_to_sigma, model_args, g_const, no_random, ode,
@@ -318,7 +336,7 @@ def _capture_step(batch, model, pos, topo, b, nb, tor_shape, no_torsion, noisy, 
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     l0 = _lib.launch_count
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, pool=_graph_pool(device)):
         tr_score, rot_score, tor_score = model(batch)[:3]
         sde_step(pos, topo, tr_score, rot_score, None if no_torsion else tor_score, vals[3:9], z_static[0], z_static[1], z_static[2])
     return graph, vals, z_static, _lib.launch_count - l0

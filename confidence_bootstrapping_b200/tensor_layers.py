@@ -22,9 +22,10 @@ from .irreps import (TPProgram, faster_tp_program, fctp_program, get_irrep_seq, 
                      parse_irreps, sh_irreps)
 
 ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
-# accumulate kernel of K3: 2 = tcgen05 3xTF32 UMMA + TMEM accumulator (default);
+# accumulate kernel of K3: 3 = tcgen05 3xTF32 UMMA with the TRANSPOSED TMEM accumulator (default; layers with more than 240
+# f-rows -- the lmax-2 confidence layers -- automatically use 2); 2 = tcgen05 with the row-major accumulator;
 # 1 = fp32 FFMA register tiles (kept for shapes outside the UMMA tile limits and for A/B measurements)
-ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "2"))
+ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "3"))
 FOLD_E_POST = True            # fold W1e.e_post[graph] into the node projection on the host (tests switch it off to cover the kernel path)
 DEBUG_KEEP_WORKSPACE = None   # tests may set this to a list to inspect the K3 accumulators
 WORKSPACE_BYTES = int(os.environ.get("CB200_WORKSPACE_MB", str(16 << 10))) << 20  # cap on the K3 accumulator workspace (180 GB of HBM3e per GPU); larger layers run in node chunks

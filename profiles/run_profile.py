@@ -24,7 +24,7 @@ args = score_model_args()
 torch.manual_seed(0)
 model = get_model(args, dev, t_to_sigma=partial(t_to_sigma, args=args), no_parallel=True).eval()
 dl = bench.build_workload(1, args, bench.SAMPLES)
-batch = Batch.from_data_list(dl).to(dev)
+batch = Batch.from_data_list(dl, device=dev)   # device collate (flags the replicated receptor) like sampling()
 with torch.no_grad():
     for i in range(n_fwd):
         set_time(batch, None, t, t, t, batch.num_graphs, False, False, dev)

@@ -217,12 +217,14 @@ def test_sde_step_vs_reference_golden():
     assert rmsd(got, want) < 1e-4
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("in_ir,sh_l,out_ir,faster,groups,nef", [
     (SEQ[3], 1, SEQ[3], True, 4, 96), (SEQ[0], 1, SEQ[1], True, 1, 96), (CONF[3], 2, CONF[3], False, 9, 72),
     (SEQ[3], 1, "2x1o + 2x1e", False, 1, 64)])
-def test_tp_conv_layer_ffma_accumulate(in_ir, sh_l, out_ir, faster, groups, nef):
-    """K3 with the fp32 FFMA accumulate kernel (accum_mode 1; the default is the tcgen05 3xTF32 kernel, which every
-    other test exercises): same 1e-5 relative bar."""
+def test_tp_conv_layer_other_accumulate_kernels(in_ir, sh_l, out_ir, faster, groups, nef, mode):
+    """K3 with the non-default accumulate kernels: accum_mode 1 = fp32 FFMA register tiles, 2 = tcgen05 3xTF32 with the
+    row-major TMEM accumulator (the default, 3, keeps the accumulator transposed and is what every other test exercises;
+    layers with more than 240 f-rows fall back to 2 by themselves).  Same 1e-5 relative bar."""
     from confidence_bootstrapping_b200 import tensor_layers
     from confidence_bootstrapping_b200.tensor_layers import TensorProductConvLayer
     from helpers import randomize_norm_stats
@@ -246,7 +248,7 @@ def test_tp_conv_layer_ffma_accumulate(in_ir, sh_l, out_ir, faster, groups, nef)
         want = om.tp_conv_layer(sd, "x", in_ir, o3.Irreps(sh_ir), out_ir, faster, groups, residual, True, x, ei, ea_list, sh, out_nodes=n_out)
         layer = layer.cuda()
         old = tensor_layers.ACCUM_MODE
-        tensor_layers.ACCUM_MODE = 1
+        tensor_layers.ACCUM_MODE = mode
         try:
             got = layer(x.cuda(), ei.cuda(), [e.cuda() for e in ea_list] if groups > 1 else ea.cuda(), sh.cuda(), out_nodes=n_out)
             torch.cuda.synchronize()
