@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcb200.so")
-SOURCES = ["cabi.cu", "radius.cu", "edge_feat.cu", "tp_conv.cu", "sde_step.cu", "crop.cu"]
+SOURCES = ["cabi.cu", "radius.cu", "edge_feat.cu", "tp_conv.cu", "sde_step.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("CB200_EXTRA_NVCC_FLAGS", "").split()
 

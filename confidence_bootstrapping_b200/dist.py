@@ -36,6 +36,19 @@ def partition_lpt(costs: Sequence[float], world_size: int) -> List[List[int]]:
     return parts
 
 
+def partition_samples(n_samples: int, world_size: int) -> List[List[int]]:
+    """Contiguous, near-equal blocks of the sample indices of ONE complex (BASELINE config 5: a single 1000-residue
+    complex x 128 samples on 8 GPUs).  Every (complex, sample) trajectory is independent (utils/sampling.py:89-233), so
+    samples shard as freely as complexes do; each rank then runs `sampling()` on its block."""
+    base, extra = divmod(n_samples, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        out.append(list(range(start, start + n)))
+        start += n
+    return out
+
+
 def _world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()

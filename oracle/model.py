@@ -10,7 +10,7 @@ index_add scatter-mean, per-call graph rebuild):
   models/score_model.py:667-677         GaussianSmearing                -> _smear
   models/score_model.py:282-449,492-664 CG TensorProductScoreModel      -> cg_forward
   models/all_atom_score_model.py:274-507,515-664 all-atom model         -> aa_forward
-Pinned against the real reference executed under oracle/shims.py (tests/golden, tests/test_oracle_vs_reference.py).
+Pinned against the real reference executed under oracle/shims.py (tests/golden, tests/test_golden_oracle.py).
 """
 from __future__ import annotations
 

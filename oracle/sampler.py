@@ -6,7 +6,7 @@
   utils/diffusion_utils.py:60-78   modify_conformer_batch               -> modify_conformer_batch
   utils/diffusion_utils.py:28-32,138-143,150-161  t_to_sigma / get_t_schedule / set_time
   utils/sampling.py:59-274         sampling (default branch + ode / temperature / no_random variants)
-Pinned against the real reference executed under oracle/shims.py (tests/test_oracle_vs_reference.py).
+Pinned against the real reference executed under oracle/shims.py (tests/test_golden_oracle.py).
 """
 from __future__ import annotations
 

@@ -23,6 +23,13 @@ def test_partition_lpt_is_deterministic_and_balanced():
     assert cbdist.partition_lpt([4.0], 4) == [[0], [], [], []]   # more ranks than complexes: empty shards are fine
 
 
+def test_partition_samples_covers_every_sample_once():
+    for n, w in ((128, 8), (10, 4), (3, 8), (0, 2)):
+        parts = cbdist.partition_samples(n, w)
+        assert len(parts) == w and sum(parts, []) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
 def _fake_result(i, n_samples):
     n_atoms = 5 + 3 * i
     g = torch.Generator().manual_seed(100 + i)

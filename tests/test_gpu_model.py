@@ -405,3 +405,80 @@ def test_shared_first_layer_receptor_messages_match_the_general_path():
         for a, b in zip(outs[k][:3], outs[k + 2][:3]):
             assert blockwise_err(a, b) < 2e-6
         assert items[k] < items[k + 2]
+
+
+def _two_gpu_worker(rank, world, port, q):
+    """One rank of the 2-GPU run of test_sharded_sampling_on_two_gpus_matches_one_gpu (spawned process)."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        poses, confs = _sharded_sample(torch.device("cuda", rank))
+        q.put((rank, [p.cpu() for p in poses], [c.cpu() for c in confs]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _sharded_sample(dev):
+    from confidence_bootstrapping_b200 import dist as cbdist
+    from confidence_bootstrapping_b200.configs import confidence_model_args, score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule, t_to_sigma as t2s_full
+    from confidence_bootstrapping_b200.sampling import randomize_position, sampling
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    from confidence_bootstrapping_b200.utils import get_model
+    args, cargs = score_model_args(), confidence_model_args()
+    t2s = partial(t2s_full, args=args)
+    torch.manual_seed(0)
+    model = get_model(args, dev, t_to_sigma=t2s, no_parallel=True).eval()
+    torch.manual_seed(1)
+    cmodel = get_model(cargs, dev, t_to_sigma=None, no_parallel=True, confidence_mode=True).eval()
+    sizes = [(260, 21), (150, 10), (410, 34), (200, 15), (330, 27)]
+    complexes = [Batch.from_data_list([make_complex(800 + i, nr, nl, all_atoms=True)]) for i, (nr, nl) in enumerate(sizes)]
+    sched = get_t_schedule("expbeta", 4, 1, 1)
+
+    def sample_fn(c, n):
+        i = next(k for k, x in enumerate(complexes) if x is c)
+        np.random.seed(i)
+        torch.manual_seed(i)
+        dl = [copy.deepcopy(c) for _ in range(n)]
+        randomize_position(dl, False, False, args.tr_sigma_max)
+        fl = copy.deepcopy(dl)
+        with injected_noise(seed=50 + i):
+            out, conf = sampling(data_list=dl, model=model, inference_steps=4, tr_schedule=sched, rot_schedule=sched, tor_schedule=sched,
+                                 device=dev, t_to_sigma=t2s, model_args=args, batch_size=n, confidence_model=cmodel,
+                                 filtering_data_list=fl, filtering_model_args=cargs)
+        return torch.stack([d["ligand"].pos for d in out]), conf
+
+    return cbdist.sample_complexes(complexes, 3, sample_fn)
+
+
+@pytest.mark.gpu
+def test_sharded_sampling_on_two_gpus_matches_one_gpu():
+    """dist.sample_complexes on real GPUs with real payloads -- LPT shards over 2 ranks (NCCL, one process per
+    GPU), variable-length all-gather of poses + confidences; every rank ends up with exactly the single-GPU results (the whole
+    path is bit-reproducible, so equality is exact)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    single_p, single_c = _sharded_sample(torch.device("cuda", 0))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, poses, confs in res:
+        for a, b in zip(poses, single_p):
+            assert torch.equal(a, b.cpu())
+        for a, b in zip(confs, single_c):
+            assert torch.equal(a, b.cpu())
