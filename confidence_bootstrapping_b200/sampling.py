@@ -176,6 +176,17 @@ _graph_warned = False
 _graph_pools = {}      # device index -> memory-pool handle shared by every step graph captured on that device
 
 
+_capture_streams = {}
+
+
+def _capture_stream(device):
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _capture_streams:
+        _capture_streams[idx] = torch.cuda.Stream(device=idx)
+    return _capture_streams[idx]
+
+
 def _graph_pool(device):
     """One private memory pool per device for all step graphs: a graph's intermediates (K3 workspaces are GBs) are carved
     from it during capture and return to it when the graph is dropped at the end of the sampling call, so the next call's
@@ -186,9 +197,13 @@ def _graph_pool(device):
         # the allocator drops a pool when the last graph captured into it dies: a tiny keeper graph pins it for the process
         pool = torch.cuda.graph_pool_handle()
         keeper = torch.cuda.CUDAGraph()
-        torch.cuda.synchronize()
-        with torch.cuda.graph(keeper, pool=pool):
+        side = _capture_stream(device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            keeper.capture_begin(pool=pool)
             anchor = torch.zeros(8, device=torch.device("cuda", idx))
+            keeper.capture_end()
+        torch.cuda.current_stream().wait_stream(side)
         _graph_pools[idx] = (pool, keeper, anchor)
     return _graph_pools[idx][0]
 
@@ -333,12 +348,23 @@ def _capture_step(batch, model, pos, topo, b, nb, tor_shape, no_torsion, noisy, 
     batch.complex_t = {"tr": vals[0:1].expand(b), "rot": vals[1:2].expand(b), "tor": vals[2:3].expand(b)}
     batch.complex_t_host = None
     batch.cb200_step = {"so3_norm": vals[9:10], "torus_norm": vals[10:11]}
-    torch.cuda.synchronize()
+    # Manual capture on a side stream instead of the torch.cuda.graph() context: that context synchronises the device,
+    # runs the garbage collector and EMPTIES the caching allocator on entry, which costs ~140 ms per sampling call once the
+    # eager steps have to cudaMalloc their multi-GB workspaces again.  Here the capture only waits (on the device) for the
+    # work already enqueued, and the host records the graph while the GPU is still busy with the eager first step.
     graph = torch.cuda.CUDAGraph()
     l0 = _lib.launch_count
-    with torch.cuda.graph(graph, pool=_graph_pool(device)):
-        tr_score, rot_score, tor_score = model(batch)[:3]
-        sde_step(pos, topo, tr_score, rot_score, None if no_torsion else tor_score, vals[3:9], z_static[0], z_static[1], z_static[2])
+    main = torch.cuda.current_stream()
+    side = _capture_stream(device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        graph.capture_begin(pool=_graph_pool(device))
+        try:
+            tr_score, rot_score, tor_score = model(batch)[:3]
+            sde_step(pos, topo, tr_score, rot_score, None if no_torsion else tor_score, vals[3:9], z_static[0], z_static[1], z_static[2])
+        finally:
+            graph.capture_end()
+    main.wait_stream(side)
     return graph, vals, z_static, _lib.launch_count - l0
 
 

