@@ -1,0 +1,504 @@
+// K3 (a''): warp-specialised accumulate kernel -- included inside namespace tc of tp_conv.cu.
+//
+// Same arithmetic as tp_accumulate_tc_kernel<true> (transposed accumulator D[h~ unit][f-row] = H~ . F^T in TMEM, 3xTF32,
+// hidden layer of the radial MLP on the tensor core, column H of the workspace summed by the f-row threads), but the chunk
+// pipeline is cut into ROLES that run concurrently on different warps of ONE CTA per SM and hand work over through
+// mbarriers only -- no CTA-wide barrier per 16 edges (those were 25 % of the warp-stall samples of the lock-step kernel,
+// profiles/r2/k3_ncu_summary_mid.txt), the chunk iterator and the operand gather run ahead on their own warp, and two
+// TMEM accumulators let the epilogue of item i overlap the chunks of item i+1:
+//
+//   warp 16      S  scheduler + gather : walks the CTA's (node, slot) items, writes a chunk descriptor and cp.async-gathers
+//                                        the raw operands (x[col], sh, e_attr, P_nbr[col]) of chunk c into stage c % NS
+//   warps 0-7    F  f-rows             : CG products of the gathered features -> F^T operand tile (hi/lo), buffer c & 1
+//   warps 8-11   H  hidden layer       : e_attr split -> hidden-layer MMA -> pre-activations back from TMEM -> + node /
+//                                        neighbour projections, ReLU, hi/lo split -> H~ operand tile, buffer c & 1;
+//                                        one thread issues every MMA of the CTA (fixed order => bit-reproducible sums)
+//   warps 12-15  E  epilogue           : finished accumulator TMEM -> registers -> coalesced global stores (workspace)
+//
+//   barrier           producer -> consumer            count
+//   raw_full[s]       S (data landed)  -> F, H        1
+//   raw_empty[s]      F, H (stage read) -> S          12 (one lane per warp)
+//   f_full[b]         F (tile written) -> H issuer    8
+//   f_free[b]         tcgen05.commit   -> F           1
+//   h_free[b]         tcgen05.commit   -> H           1
+//   hid_bar           tcgen05.commit   -> H           1
+//   acc_full[a]       tcgen05.commit   -> E           1   (or a plain arrive carrying the end-of-work sentinel)
+//   acc_empty[a]      E (TMEM read)    -> H issuer    4
+//
+// TMEM (512 columns, one CTA per SM): accumulator a at column 240 a, hidden pre-activations at 480.
+// Every wait is a bounded spin that traps instead of hanging the GPU.
+
+namespace ws {
+
+constexpr int NS = 4;                 // raw-operand stages the scheduler may run ahead
+constexpr int NI = 8;                 // item-descriptor ring (>= NS + 2 items can be open between S and E)
+constexpr int F_WARPS = 8, H_WARPS = 4, E_WARPS = 4;
+constexpr int THREADS_WS = 32 * (F_WARPS + H_WARPS + E_WARPS + 1);
+constexpr int ACC_COLS = 240;
+constexpr int TMEM_COLS_WS = 512;
+
+struct ChunkDesc { int valid, seg, n, flags, item_seq, node, q, pad; };     // flags: 1 = first chunk of its item, 2 = last
+struct ItemDesc { unsigned long long ws_off; int row_stride, valid; };
+
+struct LayoutWS {
+    int fhi[2], flo[2], hhi[2], hlo[2], ehi, elo, w1hi, w1lo, raw, rows, terms, cdesc, idesc, total;   // byte offsets
+    int raw_stage, o_xs, o_shs, o_es, o_ps;     // bytes per raw stage and offsets inside it
+    int dxp, sbow, f_groups;
+};
+
+__host__ __device__ inline LayoutWS make_layout_ws(int n_rows, int n_terms, int ne, int d_in, int S, int H) {
+    LayoutWS L;
+    auto al = [](int v, int a) { return (v + a - 1) / a * a; };
+    L.sbow = (ne / 4) * LBO;
+    L.dxp = d_in + (d_in & 1);
+    L.f_groups = (n_rows + 15) / 16 * 2;
+    int o = 0;
+    for (int b = 0; b < 2; ++b) { L.fhi[b] = o; o += L.f_groups * SBO; L.flo[b] = o; o += L.f_groups * SBO; }
+    for (int b = 0; b < 2; ++b) { L.hhi[b] = o; o += 16 * SBO; L.hlo[b] = o; o += 16 * SBO; }
+    L.ehi = o;  o += (KC / 8) * L.sbow;
+    L.elo = o;  o += (KC / 8) * L.sbow;
+    L.w1hi = o; o += 16 * L.sbow;          // full 128 rows: rows >= H stay zero (nothing may follow that a stale read could hit)
+    L.w1lo = o; o += 16 * L.sbow;
+    L.o_xs = 0;
+    L.o_shs = al(KC * L.dxp * 4, 16);
+    L.o_es = L.o_shs + al(KC * S * 4, 16);
+    L.o_ps = L.o_es + al(KC * ne * 4, 16);
+    L.raw_stage = L.o_ps + al(KC * H * 4, 16);
+    L.raw = o;  o += NS * L.raw_stage;
+    L.rows = o; o += al(n_rows * 32, 16);
+    L.terms = o; o += al(n_terms * 8, 16);
+    L.cdesc = o; o += NS * (int)sizeof(ChunkDesc);
+    L.idesc = o; o += NI * (int)sizeof(ItemDesc);
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS_WS, 1)
+tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) {
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    const int H = a.H, ne = a.ne, S = a.S, d_in = a.d_in, n_rows = a.n_rows;
+    const LayoutWS L = make_layout_ws(n_rows, a.n_terms, ne, d_in, S, H);
+    const int dxp = L.dxp, SBOW = L.sbow, HA = H + PADC;
+    const int NRP = (n_rows + 15) & ~15;
+    cb_tp_row* rows_s = reinterpret_cast<cb_tp_row*>(smraw + L.rows);
+    cb_tp_term* terms_s = reinterpret_cast<cb_tp_term*>(smraw + L.terms);
+    ChunkDesc* cdesc = reinterpret_cast<ChunkDesc*>(smraw + L.cdesc);
+    ItemDesc* idesc_ring = reinterpret_cast<ItemDesc*>(smraw + L.idesc);
+    __shared__ SlotTable st;
+    __shared__ __align__(8) uint64_t raw_full[NS], raw_empty[NS], f_full[2], f_free[2], h_free[2], hid_bar, acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- once per CTA
+    if (tid == 0) {
+        build_slots(a, st);
+        for (int s = 0; s < NS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], F_WARPS + H_WARPS); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&f_full[b], F_WARPS); mbar_init(&f_free[b], 1); mbar_init(&h_free[b], 1);
+            mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], E_WARPS);
+        }
+        mbar_init(&hid_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS_WS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    {
+        const int* src = reinterpret_cast<const int*>(a.rows);
+        int* dst = reinterpret_cast<int*>(rows_s);
+#pragma unroll 1
+        for (int i = tid; i < n_rows * 8; i += THREADS_WS) dst[i] = src[i];
+        const int2* tsrc = reinterpret_cast<const int2*>(a.terms);
+        int2* tdst = reinterpret_cast<int2*>(terms_s);
+#pragma unroll 1
+        for (int i = tid; i < a.n_terms; i += THREADS_WS) tdst[i] = tsrc[i];
+        // operand tiles start as zeros: padding rows (f-rows >= n_rows, hidden units >= H) are never written again
+#pragma unroll 1
+        for (int i = tid; i < L.raw / 16; i += THREADS_WS) reinterpret_cast<float4*>(smraw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_hid = tmem_base + 2u * ACC_COLS;
+
+    auto stage_ptr = [&](int s) { return smraw + L.raw + s * L.raw_stage; };
+
+    if (warp == F_WARPS + H_WARPS + E_WARPS) {
+        // =============================================================== S: scheduler + gather (one warp, warp-uniform control)
+        auto seg_range = [&](int seg, int node, int& e0, int& e1) { seg_edges(a.segs[seg], node, e0, e1); };
+        int item = blockIdx.x, q = 0, item_seq = -1;
+        int c = 0;                   // chunk counter of this CTA
+        int pending = 0;             // chunks whose gather has been issued but whose raw_full has not been signalled
+        bool done = false;
+#pragma unroll 1
+        while (!done) {
+            // ---- next item with at least one edge
+            int node = 0, seg = 0, e0 = 0, e1 = 0;
+            bool found = false;
+#pragma unroll 1
+            for (; item < n_items && !found; ) {
+                while (q + 1 < st.n_slots && item >= st.item_off[q + 1]) ++q;
+                node = st.lo[q] + (item - st.item_off[q]);
+#pragma unroll 1
+                for (int sg = st.first_seg[q]; sg < st.first_seg[q] + st.n_segs[q]; ++sg) {
+                    seg_range(sg, node, e0, e1);
+                    if (e1 > e0) { seg = sg; found = true; break; }
+                }
+                if (!found) item += (int)gridDim.x;
+            }
+            if (!found) {
+                done = true;
+            } else {
+                ++item_seq;
+                // where the finished tile goes: written to the item ring before the item's first chunk is published
+                int ws_stride;
+                const size_t ws_off = ws_place(a, st, q, node, n_rows, HA, lane, ws_stride);
+                if (lane == 0) {
+                    ItemDesc d; d.ws_off = (unsigned long long)ws_off; d.row_stride = ws_stride; d.valid = 1;
+                    idesc_ring[item_seq % NI] = d;
+                }
+            }
+            // ---- the item's chunks (or the end-of-work sentinel)
+            bool first = true;
+#pragma unroll 1
+            while (true) {
+                const int s = c % NS;
+                mbar_wait(&raw_empty[s], ((c / NS) & 1) ^ 1);
+                ChunkDesc d;
+                d.valid = done ? 0 : 1; d.seg = seg; d.item_seq = item_seq; d.node = node; d.q = q; d.pad = 0;
+                int n = 0, base = e0;
+                bool last = true;
+                if (!done) {
+                    n = min(KC, e1 - e0);
+                    // more edges of this item after this chunk?
+                    int nseg = seg, ne0 = e0 + KC, ne1 = e1;
+                    bool more = ne0 < ne1;
+                    if (!more) {
+#pragma unroll 1
+                        for (int sg = seg + 1; sg < st.first_seg[q] + st.n_segs[q]; ++sg) {
+                            int b0, b1;
+                            seg_range(sg, node, b0, b1);
+                            if (b1 > b0) { nseg = sg; ne0 = b0; ne1 = b1; more = true; break; }
+                        }
+                    }
+                    last = !more;
+                    d.n = n; d.flags = (first ? 1 : 0) | (last ? 2 : 0);
+                    // gather the raw operands of the chunk (lands asynchronously; published two chunks later)
+                    const cb_tp_segment& sg = a.segs[seg];
+                    unsigned char* stg = stage_ptr(s);
+                    float* xs = reinterpret_cast<float*>(stg + L.o_xs);
+                    float* shs = reinterpret_cast<float*>(stg + L.o_shs);
+                    float* es = reinterpret_cast<float*>(stg + L.o_es);
+                    float* ps = reinterpret_cast<float*>(stg + L.o_ps);
+                    const int mycol = lane < n ? __ldg(sg.col + base + lane) + sg.col_off : 0;
+#pragma unroll 1
+                    for (int e = 0; e < n; ++e) {
+                        const int col = __shfl_sync(0xffffffffu, mycol, e);
+                        const float* xr = a.x + (size_t)col * d_in;
+#pragma unroll 1
+                        for (int k = lane; k < d_in / 2; k += 32) cp_async_bytes8(xs + e * dxp + 2 * k, xr + 2 * k);
+                        if (sg.P_nbr) {
+                            const float* pr = sg.P_nbr + (size_t)col * sg.ldp_nbr;
+#pragma unroll 1
+                            for (int k = lane; k < H / 4; k += 32) cp_async_bytes16(ps + e * H + 4 * k, pr + 4 * k);
+                        }
+                    }
+#pragma unroll 1
+                    for (int i = lane; i < n * S; i += 32) cp_async_bytes4(shs + i, sg.sh + (size_t)base * S + i);
+#pragma unroll 1
+                    for (int i = lane; i < n * (ne / 4); i += 32) cp_async_bytes16(es + 4 * i, sg.e_attr + (size_t)base * ne + 4 * i);
+                    seg = nseg; e0 = ne0; e1 = ne1;
+                } else {
+                    d.n = 0; d.flags = 0;
+                }
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+                if (lane == 0) cdesc[s] = d;
+                ++pending;
+                ++c;
+                // publish the chunk issued NS-2 iterations ago: its copies (every lane's) have landed
+                if (pending > NS - 2) {
+                    asm volatile("cp.async.wait_group %0;\n" ::"n"(NS - 2) : "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&raw_full[(c - 1 - (NS - 2)) % NS]);
+                    --pending;
+                }
+                first = false;
+                if (done || last) break;
+            }
+            if (!done) item += (int)gridDim.x;
+        }
+        // drain: publish what is still pending (the sentinel included)
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+#pragma unroll 1
+        for (; pending > 0; --pending)
+            if (lane == 0) mbar_arrive(&raw_full[(c - pending) % NS]);
+    } else if (warp < F_WARPS) {
+        // =============================================================== F: f-rows -> F^T operand tiles
+        int tb0 = 0, te0 = 0, t_xi[MAXT], t_si[MAXT];
+        float t_cf[MAXT];
+        if (tid < n_rows) { tb0 = rows_s[tid].term_begin; te0 = rows_s[tid].term_end; }
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t) {
+            const bool on = tid < n_rows && tb0 + t < te0;
+            const cb_tp_term tm = on ? terms_s[tb0 + t] : cb_tp_term{0, 0, 0.0f};
+            t_xi[t] = tm.x_idx; t_si[t] = tm.sh_idx; t_cf[t] = on ? tm.coef : 0.0f;
+        }
+        const int nt_warp = __reduce_max_sync(0xffffffffu, min(te0 - tb0, MAXT));
+        float fsum = 0.0f;
+#pragma unroll 1
+        for (int c = 0;; ++c) {
+            const int s = c % NS, fb = c & 1;
+            mbar_wait(&raw_full[s], (c / NS) & 1);
+            const ChunkDesc d = cdesc[s];
+            if (!d.valid) break;
+            mbar_wait(&f_free[fb], ((c >> 1) & 1) ^ 1);         // the MMAs that read this tile buffer two chunks ago are done
+            const unsigned char* stg = stage_ptr(s);
+            const float* xs = reinterpret_cast<const float*>(stg + L.o_xs);
+            const float* shs = reinterpret_cast<const float*>(stg + L.o_shs);
+            const int n = d.n, nq = 2 * ((n + 7) >> 3);
+            if (tid < n_rows) {
+                const FRowCtx fc{xs, shs, terms_s, smraw + L.fhi[fb], smraw + L.flo[fb], dxp, S, n, nq, tb0, te0, (tid >> 3) * SBO + (tid & 7) * 16};
+                float part;
+                switch (nt_warp) {
+                    case 1: part = f_row<1>(fc, t_xi, t_si, t_cf); break;
+                    case 2: part = f_row<2>(fc, t_xi, t_si, t_cf); break;
+                    case 3: part = f_row<3>(fc, t_xi, t_si, t_cf); break;
+                    default: part = f_row<MAXT>(fc, t_xi, t_si, t_cf); break;
+                }
+                fsum = (d.flags & 1) ? part : fsum + part;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy tile writes -> async proxy (UMMA)
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&f_full[fb]); mbar_arrive(&raw_empty[s]); }
+            if ((d.flags & 2) && tid < n_rows) {       // column H of the workspace: sum_e f_e[r], then the zero pad the transform multiplies by 0
+                const ItemDesc it = idesc_ring[d.item_seq % NI];
+                *reinterpret_cast<float4*>(a.workspace + it.ws_off + (size_t)tid * it.row_stride + H) = make_float4(fsum, 0.f, 0.f, 0.f);
+            }
+        }
+    } else if (warp < F_WARPS + H_WARPS) {
+        // =============================================================== H: hidden layer, H~ tiles, MMA issue
+        const int ht = tid - 32 * F_WARPS;          // 0..127 = hidden unit = TMEM lane
+        const int lg = warp & 3;                    // == ht >> 5 (warp 8 is lane group 0)
+        const bool issuer = ht == 0;
+        unsigned char* Ehi = smraw + L.ehi; unsigned char* Elo = smraw + L.elo;
+        unsigned char* W1hi = smraw + L.w1hi; unsigned char* W1lo = smraw + L.w1lo;
+        const uint64_t d_w1hi = make_desc_sbo(smem_u32(W1hi), SBOW), d_w1lo = make_desc_sbo(smem_u32(W1lo), SBOW);
+        const uint64_t d_ehi = make_desc_sbo(smem_u32(Ehi), SBOW), d_elo = make_desc_sbo(smem_u32(Elo), SBOW);
+        uint64_t d_fhi[2], d_flo[2], d_hhi[2], d_hlo[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            d_fhi[b] = make_desc(smem_u32(smraw + L.fhi[b])); d_flo[b] = make_desc(smem_u32(smraw + L.flo[b]));
+            d_hhi[b] = make_desc(smem_u32(smraw + L.hhi[b])); d_hlo[b] = make_desc(smem_u32(smraw + L.hlo[b]));
+        }
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NRP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_h = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        int staged_slot = -1, hb_q = -1, hb_graph = -1;
+        float hb_const = 0.0f, hb = 0.0f;
+#pragma unroll 1
+        for (int c = 0;; ++c) {
+            const int s = c % NS, b = c & 1;
+            mbar_wait(&raw_full[s], (c / NS) & 1);
+            const ChunkDesc d = cdesc[s];
+            if (!d.valid) {
+                // end of work: hand the sentinel to the epilogue warps through the next accumulator's barrier
+                if (issuer) {
+                    const int seq = d.item_seq + 1;
+                    // flow control like a real item: the epilogue must have consumed (hence observed) the previous phase of
+                    // this barrier before the sentinel completes the next one
+                    mbar_wait(&acc_empty[seq & 1], ((seq >> 1) & 1) ^ 1);
+                    ItemDesc it; it.ws_off = 0; it.row_stride = 0; it.valid = 0;
+                    idesc_ring[seq % NI] = it;
+                    asm volatile("fence.acq_rel.cta;" ::: "memory");
+                    mbar_arrive(&acc_full[seq & 1]);
+                }
+                break;
+            }
+            const cb_tp_segment& sg = a.segs[d.seg];
+            const unsigned char* stg = stage_ptr(s);
+            const float* es = reinterpret_cast<const float*>(stg + L.o_es);
+            const float* Ps = reinterpret_cast<const float*>(stg + L.o_ps);
+            const int n = d.n, ksteps = (n + 7) >> 3;
+            if (d.flags & 1) {
+                // ---- per-item constants: first Linear's edge-embedding slice as operand tiles (on slot change), bias + node projection
+                const cb_tp_segment& s0 = a.segs[st.first_seg[d.q]];
+                if (staged_slot != d.q) {           // block-uniform within the role: no hidden-layer MMA is in flight here
+#pragma unroll 1
+                    for (int i = ht; i < H * (ne / 4); i += 32 * H_WARPS) {
+                        const int qq = i / (ne / 4), c4 = i - qq * (ne / 4);
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(s0.W1e + (size_t)qq * s0.ldw1) + c4);
+                        float4 hi, lo;
+                        split_tf32(w.x, hi.x, lo.x); split_tf32(w.y, hi.y, lo.y); split_tf32(w.z, hi.z, lo.z); split_tf32(w.w, hi.w, lo.w);
+                        const int off = (qq >> 3) * SBOW + c4 * LBO + (qq & 7) * 16;
+                        *reinterpret_cast<float4*>(W1hi + off) = hi;
+                        *reinterpret_cast<float4*>(W1lo + off) = lo;
+                    }
+                    staged_slot = d.q;
+                }
+                if (ht < H) {
+                    const int graph = a.agg_graph ? __ldg(a.agg_graph + d.node) : 0;
+                    if (hb_q != d.q || (s0.e_post && hb_graph != graph)) {
+                        float v = __ldg(s0.b1 + ht);
+                        if (s0.e_post) {
+                            const float* ep = s0.e_post + (size_t)graph * ne;
+#pragma unroll 4
+                            for (int k = 0; k < ne; ++k) v = fmaf(__ldg(s0.W1e + (size_t)ht * s0.ldw1 + k), __ldg(ep + k), v);
+                        }
+                        hb_const = v; hb_q = d.q; hb_graph = graph;
+                    }
+                    hb = hb_const + (s0.P_agg ? __ldg(s0.P_agg + (size_t)d.node * s0.ldp_agg + ht) : 0.0f);
+                }
+            }
+            // ---- edge-embedding rows of the chunk as hi/lo B tiles of the hidden-layer MMA
+#pragma unroll 1
+            for (int i = ht; i < KC * (ne / 4); i += 32 * H_WARPS) {
+                const int e = i / (ne / 4), c4 = i - e * (ne / 4);
+                const float4 v = *reinterpret_cast<const float4*>(es + e * ne + 4 * c4);     // rows >= n hold stale data: discarded below
+                float4 hi, lo;
+                split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+                const int off = (e >> 3) * SBOW + c4 * LBO + (e & 7) * 16;
+                *reinterpret_cast<float4*>(Ehi + off) = hi;
+                *reinterpret_cast<float4*>(Elo + off) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            named_bar_sync(1, 32 * H_WARPS);
+            if (issuer) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint64_t dwh = d_w1hi, dwl = d_w1lo, deh = d_ehi, del = d_elo;
+#pragma unroll 2
+                for (int ks = 0; ks < ne / 8; ++ks) {
+                    mma_tf32(tmem_hid, dwh, deh, idesc_h, ks > 0 ? 1u : 0u);
+                    mma_tf32(tmem_hid, dwh, del, idesc_h, 1u);
+                    mma_tf32(tmem_hid, dwl, deh, idesc_h, 1u);
+                    dwh += (2 * LBO) >> 4; dwl += (2 * LBO) >> 4; deh += (2 * LBO) >> 4; del += (2 * LBO) >> 4;
+                }
+                umma_commit(&hid_bar);
+            }
+            mbar_wait(&hid_bar, c & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t v[16];
+            {
+                const uint32_t taddr = tmem_hid + ((uint32_t)(lg * 32) << 16);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+            mbar_wait(&h_free[b], ((c >> 1) & 1) ^ 1);        // the MMAs that read this H~ buffer two chunks ago are done
+            if (ht < H) {
+                unsigned char* Hhi = smraw + L.hhi[b]; unsigned char* Hlo = smraw + L.hlo[b];
+                const int rbase = (ht >> 3) * SBO + (ht & 7) * 16;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float h[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int e = 4 * g + j;
+                        float pre = __uint_as_float(v[e]) + hb;
+                        if (sg.P_nbr) pre += Ps[e * H + ht];
+                        h[j] = e < n ? fmaxf(pre, 0.0f) : 0.0f;
+                    }
+                    float4 hi, lo;
+                    split_tf32(h[0], hi.x, lo.x); split_tf32(h[1], hi.y, lo.y); split_tf32(h[2], hi.z, lo.z); split_tf32(h[3], hi.w, lo.w);
+                    *reinterpret_cast<float4*>(Hhi + rbase + g * LBO) = hi;
+                    *reinterpret_cast<float4*>(Hlo + rbase + g * LBO) = lo;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[s]);
+            named_bar_sync(1, 32 * H_WARPS);
+            if (issuer) {
+                const int acc = d.item_seq & 1;
+                mbar_wait(&f_full[b], (c >> 1) & 1);
+                if (d.flags & 1) mbar_wait(&acc_empty[acc], ((d.item_seq >> 1) & 1) ^ 1);   // the epilogue of item_seq - 2 has drained it
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t dacc = tmem_base + (uint32_t)(acc * ACC_COLS);
+                const uint32_t acc0 = (d.flags & 1) ? 0u : 1u;
+                mma_tf32(dacc, d_hhi[b], d_fhi[b], idesc, acc0);
+                mma_tf32(dacc, d_hhi[b], d_flo[b], idesc, 1u);
+                mma_tf32(dacc, d_hlo[b], d_fhi[b], idesc, 1u);
+                if (ksteps > 1) {
+                    const uint64_t ks = (uint64_t)((2 * LBO) >> 4);
+                    mma_tf32(dacc, d_hhi[b] + ks, d_fhi[b] + ks, idesc, 1u);
+                    mma_tf32(dacc, d_hhi[b] + ks, d_flo[b] + ks, idesc, 1u);
+                    mma_tf32(dacc, d_hlo[b] + ks, d_fhi[b] + ks, idesc, 1u);
+                }
+                umma_commit(&f_free[b]);
+                umma_commit(&h_free[b]);
+                if (d.flags & 2) umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        // =============================================================== E: epilogue (TMEM -> registers -> workspace)
+        const int lg = warp & 3;                    // warp 12 is lane group 0
+        const int j = lg * 32 + lane;
+#pragma unroll 1
+        for (int item_seq = 0;; ++item_seq) {
+            const int acc = item_seq & 1;
+            mbar_wait(&acc_full[acc], (item_seq >> 1) & 1);
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            const ItemDesc it = idesc_ring[item_seq % NI];
+            if (!it.valid) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lg * 32 < H) {                      // warp-uniform: lane groups beyond the hidden width hold nothing
+                float* dst = a.workspace + it.ws_off + j;
+                const int row_stride = it.row_stride;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NRP; c0 += 32) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_COLS + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                        : "r"(taddr));
+                    const bool second = c0 + 16 < NRP;
+                    if (second)
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                            : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                            : "r"(taddr + 16u));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (j < H) {
+                        const int nr = min(second ? 32 : 16, n_rows - c0);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nr) dst[(size_t)(c0 + i) * row_stride] = __uint_as_float(v[i]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS_WS));
+    }
+}
+
+}  // namespace ws

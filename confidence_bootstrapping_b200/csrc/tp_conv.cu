@@ -1063,6 +1063,8 @@ tp_accumulate_tc_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     }
 }
 
+#include "tp_accumulate_ws.cuh"
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------ (b)
@@ -1571,14 +1573,33 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
                      "cb_tp_conv_forward: workspace too small (%lld floats for %lld accumulators)",
                      (long long)a->workspace_floats, (long long)ws_items);
         int rc;
-        if (a->accum_mode == 2 || a->accum_mode == 3) {
+        bool ws_ok = false;
+        if (a->accum_mode == 4) {
+            // warp-specialised kernel (tp_accumulate_ws.cuh): transposed accumulator, 1 CTA per SM, 512 TMEM columns
+            const tc::ws::LayoutWS LW = tc::ws::make_layout_ws(R, a->n_terms, a->ne, a->d_in, a->S, H);
+            ws_ok = R <= tc::ws::ACC_COLS && H % 32 == 0 && H <= 128 && a->ne % 8 == 0 && a->d_in % 2 == 0 && LW.total <= 225 * 1024;
+            if (ws_ok) {
+                const size_t smem = (size_t)LW.total;
+                cudaError_t e = cudaFuncSetAttribute(tc::ws::tp_accumulate_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) {
+                    cb_set_error("cb_tp_conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                    return CB_ERR_CUDA;
+                }
+                const int grid = items < CB_NUM_SMS ? (int)items : CB_NUM_SMS;
+                tc::ws::tp_accumulate_ws_kernel<<<grid, tc::ws::THREADS_WS, smem, st>>>(*a, (int)items);
+                CB_CHECK_LAUNCH("cb_tp_conv_forward(accumulate, warp-specialised)");
+                rc = CB_OK;
+            }
+        }
+        if (ws_ok) {
+        } else if (a->accum_mode >= 2) {
             CB_CHECK_ARG(a->d_in % 2 == 0, "cb_tp_conv_forward: tcgen05 accumulate needs an even node-feature width (d_in=%d)", a->d_in);
             CB_CHECK_ARG(R <= 384 && ((R + 127) / 128) * ((H + 1 + 15) / 16 * 16) + tc::KC <= tc::TMEM_COLS,
                          "cb_tp_conv_forward: tcgen05 accumulate supports rows<=384 and tiles within 256 TMEM columns (rows=%d H=%d)", R, H);
             CB_CHECK_ARG(a->ne % 8 == 0 && H <= 120, "cb_tp_conv_forward: tcgen05 accumulate needs ne %% 8 == 0 and H <= 120 (ne=%d H=%d)", a->ne, H);
             // transposed accumulator (no shared-memory epilogue) whenever the f-rows fit 240 TMEM columns and the hidden width
             // is a multiple of 32 (a lane group is either full or empty)
-            const bool transposed = a->accum_mode == 3 && R <= 240 && H % 32 == 0 && H <= 128;
+            const bool transposed = a->accum_mode >= 3 && R <= 240 && H % 32 == 0 && H <= 128;
             const tc::Layout L = tc::make_layout(R, a->n_terms, a->ne, a->d_in, a->S, H, transposed);
             // at least 80 KB so that never more than 2 CTAs (2 x 256 TMEM columns) share an SM
             const size_t smem = (size_t)(L.total > 80 * 1024 ? L.total : 80 * 1024);

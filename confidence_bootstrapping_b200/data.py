@@ -97,6 +97,12 @@ class HeteroData:
     def __setattr__(self, name, value):
         self._g[name] = value
 
+    def __delattr__(self, name):
+        g = object.__getattribute__(self, "_g")
+        if name not in g:
+            raise AttributeError(name)
+        del g[name]
+
     def __contains__(self, name):
         return name in self._g
 

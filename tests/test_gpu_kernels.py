@@ -217,7 +217,7 @@ def test_sde_step_vs_reference_golden():
     assert rmsd(got, want) < 1e-4
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("in_ir,sh_l,out_ir,faster,groups,nef", [
     (SEQ[3], 1, SEQ[3], True, 4, 96), (SEQ[0], 1, SEQ[1], True, 1, 96), (CONF[3], 2, CONF[3], False, 9, 72),
     (SEQ[3], 1, "2x1o + 2x1e", False, 1, 64)])

@@ -336,3 +336,51 @@ def test_fast_knn_radius_edges_equal_the_dense_loop():
     for seed, n, cutoff, mx in [(0, 300, 15.0, 24), (1, 120, 15.0, 24), (2, 900, 5.0, 8), (3, 5, 15.0, 24), (4, 60, 3.0, 8), (5, 2, 1.0, 8)]:
         pos = np.random.default_rng(seed).normal(size=(n, 3)) * (n ** (1 / 3)) * 3
         assert np.array_equal(_knn_radius_edges(pos, cutoff, mx), _knn_radius_edges_fast(pos, cutoff, mx)), (seed, n)
+
+
+def test_cb_buffer_matches_the_reference_class():
+    """bootstrapping/buffer.py:CBBuffer: the cb200 class driven through the same seeded add / get sequence
+    as the REAL reference class (golden recorded under oracle/shims.py by oracle/make_buffer_golden.py) holds the same
+    complexes with the same confidence / iteration stamps after every round, reports the same length and hands out the same
+    samples -- for the plain buffer, the per-couple top-k with decay, softmax sampling at fixed length, and reset mode."""
+    import os
+    from confidence_bootstrapping_b200.bootstrapping import CBBuffer
+    from confidence_bootstrapping_b200.data import HeteroData
+    from helpers import GOLDEN
+    g = torch.load(os.path.join(GOLDEN, "cb_buffer.pt"), weights_only=False)
+
+    def fake(name, tag):
+        c = HeteroData()
+        c.name = [name]
+        c.tag = tag
+        c["ligand"].pos = torch.full((5, 3), float(tag))
+        c["receptor"].pos = torch.zeros(7, 3)
+        return c
+
+    for case in g["cases"]:
+        buf = CBBuffer(cluster_name="c0", ligand_names=g["names"], **case["kwargs"])
+        for new, want in zip(case["rounds"], case["trace"]):
+            buf.add_complexes([(fake(n, t), torch.tensor(c)) for n, t, c in new])
+            held = [(int(c.tag), float(c.confidence), int(c.iteration)) for c in buf.complexes]
+            assert held == want["held"], case["kwargs"]
+            assert buf.len() == want["len"] and buf.ligand_cnt == want["cnt"]
+            np.random.seed(case["get_seed"])
+            got = [buf.get(i) for i in range(min(6, buf.len()))]
+            assert [int(c.tag) for c in got] == want["got"]
+            assert all(not hasattr(c, "confidence") and not hasattr(c, "iteration") for c in got)
+        assert float(buf.complexes[0].complex_t["tr"]) == 0.0 and buf.complexes[0]["ligand"].node_t["rot"].shape == (5,)
+
+
+def test_select_confident_and_plain_rmsd():
+    """finetune_train.py:216,223-232: poses above the confidence cutoff (first column of a multi-class head), plain RMSD."""
+    from confidence_bootstrapping_b200.bootstrapping import plain_rmsd, select_confident
+    preds = [f"pose{i}" for i in range(5)]
+    conf = torch.tensor([0.3, -1.0, 2.5, 0.0, 0.31])
+    kept = select_confident(preds, conf, 0.3)
+    assert [p for p, _ in kept] == ["pose2", "pose4"] and float(kept[0][1]) == 2.5
+    multi = torch.stack([conf, conf.flip(0)], 1)
+    assert [p for p, _ in select_confident(preds, multi, 0.3, multi_class=True)] == ["pose2", "pose4"]
+    assert select_confident(preds, None, 0.0) == []
+    pos = torch.zeros(2, 4, 3)
+    pos[1, :, 0] = 2.0
+    assert torch.allclose(plain_rmsd(pos, torch.zeros(4, 3)), torch.tensor([0.0, 2.0]))
