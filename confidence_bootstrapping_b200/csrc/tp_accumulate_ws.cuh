@@ -7,23 +7,29 @@
 // profiles/r2/k3_ncu_summary_mid.txt), the chunk iterator and the operand gather run ahead on their own warp, and two
 // TMEM accumulators let the epilogue of item i overlap the chunks of item i+1:
 //
-//   warp 16      S  scheduler + gather : walks the CTA's (node, slot) items, writes a chunk descriptor and cp.async-gathers
-//                                        the raw operands (x[col], sh, e_attr, P_nbr[col]) of chunk c into stage c % NS
+//   warp 20      S  scheduler          : walks the CTA's (node, slot) items; per chunk of 16 edges a descriptor + the 16
+//                                        neighbour indices into stage c % NS (a single warp issuing the whole gather was
+//                                        the bottleneck of the first version: 1300 instructions per chunk at one warp's
+//                                        issue rate, every other role starved -- profiles/r2)
+//   warps 21-24  G  gather             : cp.async the raw operands (x[col], sh, e_attr, P_nbr[col]) of the chunk, four
+//                                        edges per warp, published two chunks later when the copies have landed
 //   warps 0-7    F  f-rows             : CG products of the gathered features -> F^T operand tile (hi/lo), buffer c & 1
 //   warps 8-11   H  hidden layer       : e_attr split -> hidden-layer MMA -> pre-activations back from TMEM -> + node /
 //                                        neighbour projections, ReLU, hi/lo split -> H~ operand tile, buffer c & 1;
 //                                        one thread issues every MMA of the CTA (fixed order => bit-reproducible sums)
-//   warps 12-15  E  epilogue           : finished accumulator TMEM -> registers -> coalesced global stores (workspace)
+//   warps 12-19  E  epilogue           : finished accumulator TMEM -> registers -> coalesced global stores (workspace);
+//                                        two warps per TMEM lane group, each takes half of the f-row columns
 //
 //   barrier           producer -> consumer            count
-//   raw_full[s]       S (data landed)  -> F, H        1
+//   desc_full[s]      S (descriptor)   -> G           1
+//   raw_full[s]       G (data landed)  -> F, H        4
 //   raw_empty[s]      F, H (stage read) -> S          12 (one lane per warp)
 //   f_full[b]         F (tile written) -> H issuer    8
 //   f_free[b]         tcgen05.commit   -> F           1
 //   h_free[b]         tcgen05.commit   -> H           1
 //   hid_bar           tcgen05.commit   -> H           1
 //   acc_full[a]       tcgen05.commit   -> E           1   (or a plain arrive carrying the end-of-work sentinel)
-//   acc_empty[a]      E (TMEM read)    -> H issuer    4
+//   acc_empty[a]      E (TMEM read)    -> H issuer    8
 //
 // TMEM (512 columns, one CTA per SM): accumulator a at column 240 a, hidden pre-activations at 480.
 // Every wait is a bounded spin that traps instead of hanging the GPU.
@@ -32,8 +38,8 @@ namespace ws {
 
 constexpr int NS = 4;                 // raw-operand stages the scheduler may run ahead
 constexpr int NI = 8;                 // item-descriptor ring (>= NS + 2 items can be open between S and E)
-constexpr int F_WARPS = 8, H_WARPS = 4, E_WARPS = 4;
-constexpr int THREADS_WS = 32 * (F_WARPS + H_WARPS + E_WARPS + 1);
+constexpr int F_WARPS = 8, H_WARPS = 4, E_WARPS = 8, G_WARPS = 4;
+constexpr int THREADS_WS = 32 * (F_WARPS + H_WARPS + E_WARPS + 1 + G_WARPS);
 constexpr int ACC_COLS = 240;
 constexpr int TMEM_COLS_WS = 512;
 
@@ -59,8 +65,8 @@ __host__ __device__ inline LayoutWS make_layout_ws(int n_rows, int n_terms, int 
     L.elo = o;  o += (KC / 8) * L.sbow;
     L.w1hi = o; o += 16 * L.sbow;          // full 128 rows: rows >= H stay zero (nothing may follow that a stale read could hit)
     L.w1lo = o; o += 16 * L.sbow;
-    L.o_xs = 0;
-    L.o_shs = al(KC * L.dxp * 4, 16);
+    L.o_xs = 64;                           // the stage starts with the chunk's 16 neighbour indices
+    L.o_shs = L.o_xs + al(KC * L.dxp * 4, 16);
     L.o_es = L.o_shs + al(KC * S * 4, 16);
     L.o_ps = L.o_es + al(KC * ne * 4, 16);
     L.raw_stage = L.o_ps + al(KC * H * 4, 16);
@@ -71,6 +77,22 @@ __host__ __device__ inline LayoutWS make_layout_ws(int n_rows, int n_terms, int 
     L.idesc = o; o += NI * (int)sizeof(ItemDesc);
     L.total = o;
     return L;
+}
+
+// bounded wait: a lost arrival traps after ~1.5 s of spinning instead of hanging the GPU (the kernel itself runs ~1 ms)
+__device__ __forceinline__ void mbar_wait_ws(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (unsigned spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+        if (ok) return;
+        if ((spin & 255u) == 255u && clock64() - t0 > 3000000000ll) __trap();
+    }
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -98,7 +120,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     ChunkDesc* cdesc = reinterpret_cast<ChunkDesc*>(smraw + L.cdesc);
     ItemDesc* idesc_ring = reinterpret_cast<ItemDesc*>(smraw + L.idesc);
     __shared__ SlotTable st;
-    __shared__ __align__(8) uint64_t raw_full[NS], raw_empty[NS], f_full[2], f_free[2], h_free[2], hid_bar, acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t desc_full[NS], raw_full[NS], raw_empty[NS], f_full[2], f_free[2], h_free[2], hid_bar, acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -106,7 +128,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     // ---- once per CTA
     if (tid == 0) {
         build_slots(a, st);
-        for (int s = 0; s < NS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], F_WARPS + H_WARPS); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&desc_full[s], 1); mbar_init(&raw_full[s], G_WARPS); mbar_init(&raw_empty[s], F_WARPS + H_WARPS); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&f_full[b], F_WARPS); mbar_init(&f_free[b], 1); mbar_init(&h_free[b], 1);
             mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], E_WARPS);
@@ -142,11 +164,10 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     auto stage_ptr = [&](int s) { return smraw + L.raw + s * L.raw_stage; };
 
     if (warp == F_WARPS + H_WARPS + E_WARPS) {
-        // =============================================================== S: scheduler + gather (one warp, warp-uniform control)
+        // =============================================================== S: scheduler (one warp, warp-uniform control)
         auto seg_range = [&](int seg, int node, int& e0, int& e1) { seg_edges(a.segs[seg], node, e0, e1); };
         int item = blockIdx.x, q = 0, item_seq = -1;
         int c = 0;                   // chunk counter of this CTA
-        int pending = 0;             // chunks whose gather has been issued but whose raw_full has not been signalled
         bool done = false;
 #pragma unroll 1
         while (!done) {
@@ -181,13 +202,13 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
 #pragma unroll 1
             while (true) {
                 const int s = c % NS;
-                mbar_wait(&raw_empty[s], ((c / NS) & 1) ^ 1);
+                mbar_wait_ws(&raw_empty[s], ((c / NS) & 1) ^ 1);
                 ChunkDesc d;
-                d.valid = done ? 0 : 1; d.seg = seg; d.item_seq = item_seq; d.node = node; d.q = q; d.pad = 0;
-                int n = 0, base = e0;
+                d.valid = done ? 0 : 1; d.seg = seg; d.item_seq = item_seq; d.node = node; d.q = q; d.pad = e0;   // pad = first edge
                 bool last = true;
+                d.n = 0; d.flags = 0;
                 if (!done) {
-                    n = min(KC, e1 - e0);
+                    const int n = min(KC, e1 - e0);
                     // more edges of this item after this chunk?
                     int nseg = seg, ne0 = e0 + KC, ne1 = e1;
                     bool more = ne0 < ne1;
@@ -201,56 +222,73 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     }
                     last = !more;
                     d.n = n; d.flags = (first ? 1 : 0) | (last ? 2 : 0);
-                    // gather the raw operands of the chunk (lands asynchronously; published two chunks later)
                     const cb_tp_segment& sg = a.segs[seg];
-                    unsigned char* stg = stage_ptr(s);
-                    float* xs = reinterpret_cast<float*>(stg + L.o_xs);
-                    float* shs = reinterpret_cast<float*>(stg + L.o_shs);
-                    float* es = reinterpret_cast<float*>(stg + L.o_es);
-                    float* ps = reinterpret_cast<float*>(stg + L.o_ps);
-                    const int mycol = lane < n ? __ldg(sg.col + base + lane) + sg.col_off : 0;
-#pragma unroll 1
-                    for (int e = 0; e < n; ++e) {
-                        const int col = __shfl_sync(0xffffffffu, mycol, e);
-                        const float* xr = a.x + (size_t)col * d_in;
-#pragma unroll 1
-                        for (int k = lane; k < d_in / 2; k += 32) cp_async_bytes8(xs + e * dxp + 2 * k, xr + 2 * k);
-                        if (sg.P_nbr) {
-                            const float* pr = sg.P_nbr + (size_t)col * sg.ldp_nbr;
-#pragma unroll 1
-                            for (int k = lane; k < H / 4; k += 32) cp_async_bytes16(ps + e * H + 4 * k, pr + 4 * k);
-                        }
-                    }
-#pragma unroll 1
-                    for (int i = lane; i < n * S; i += 32) cp_async_bytes4(shs + i, sg.sh + (size_t)base * S + i);
-#pragma unroll 1
-                    for (int i = lane; i < n * (ne / 4); i += 32) cp_async_bytes16(es + 4 * i, sg.e_attr + (size_t)base * ne + 4 * i);
+                    if (lane < KC) reinterpret_cast<int*>(stage_ptr(s))[lane] = lane < n ? __ldg(sg.col + e0 + lane) + sg.col_off : 0;
                     seg = nseg; e0 = ne0; e1 = ne1;
-                } else {
-                    d.n = 0; d.flags = 0;
                 }
-                asm volatile("cp.async.commit_group;\n" ::: "memory");
                 if (lane == 0) cdesc[s] = d;
-                ++pending;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&desc_full[s]);
                 ++c;
-                // publish the chunk issued NS-2 iterations ago: its copies (every lane's) have landed
-                if (pending > NS - 2) {
-                    asm volatile("cp.async.wait_group %0;\n" ::"n"(NS - 2) : "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&raw_full[(c - 1 - (NS - 2)) % NS]);
-                    --pending;
-                }
                 first = false;
                 if (done || last) break;
             }
             if (!done) item += (int)gridDim.x;
+        }
+    } else if (warp > F_WARPS + H_WARPS + E_WARPS) {
+        // =============================================================== G: gather warps (edges g, g+4, g+8, g+12 of every chunk)
+        const int g = warp - (F_WARPS + H_WARPS + E_WARPS + 1);
+        int pending = 0;
+        int c = 0;
+#pragma unroll 1
+        for (;; ++c) {
+            const int s = c % NS;
+            mbar_wait_ws(&desc_full[s], (c / NS) & 1);
+            const ChunkDesc d = cdesc[s];
+            if (d.valid) {
+                const cb_tp_segment& sg = a.segs[d.seg];
+                unsigned char* stg = stage_ptr(s);
+                const int* cols = reinterpret_cast<const int*>(stg);
+                float* xs = reinterpret_cast<float*>(stg + L.o_xs);
+                float* shs = reinterpret_cast<float*>(stg + L.o_shs);
+                float* es = reinterpret_cast<float*>(stg + L.o_es);
+                float* ps = reinterpret_cast<float*>(stg + L.o_ps);
+                const int n = d.n, base = d.pad;
+#pragma unroll 1
+                for (int e = g; e < n; e += G_WARPS) {
+                    const int col = cols[e];
+                    const float* xr = a.x + (size_t)col * d_in;
+                    float* xd = xs + e * dxp;
+#pragma unroll 1
+                    for (int k = lane; k < d_in / 2; k += 32) cp_async_bytes8(xd + 2 * k, xr + 2 * k);
+                    if (sg.P_nbr) {
+                        const float* pr = sg.P_nbr + (size_t)col * sg.ldp_nbr;
+#pragma unroll 1
+                        for (int k = lane; k < H / 4; k += 32) cp_async_bytes16(ps + e * H + 4 * k, pr + 4 * k);
+                    }
+                }
+#pragma unroll 1
+                for (int i = g * 32 + lane; i < n * S; i += 32 * G_WARPS) cp_async_bytes4(shs + i, sg.sh + (size_t)base * S + i);
+#pragma unroll 1
+                for (int i = g * 32 + lane; i < n * (ne / 4); i += 32 * G_WARPS) cp_async_bytes16(es + 4 * i, sg.e_attr + (size_t)base * ne + 4 * i);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            ++pending;
+            // publish the chunk issued NS-2 iterations ago: this warp's copies for it have landed
+            if (pending > NS - 2) {
+                asm volatile("cp.async.wait_group %0;\n" ::"n"(NS - 2) : "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_full[(c - (NS - 2)) % NS]);
+                --pending;
+            }
+            if (!d.valid) break;
         }
         // drain: publish what is still pending (the sentinel included)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncwarp();
 #pragma unroll 1
         for (; pending > 0; --pending)
-            if (lane == 0) mbar_arrive(&raw_full[(c - pending) % NS]);
+            if (lane == 0) mbar_arrive(&raw_full[(c + 1 - pending) % NS]);
     } else if (warp < F_WARPS) {
         // =============================================================== F: f-rows -> F^T operand tiles
         int tb0 = 0, te0 = 0, t_xi[MAXT], t_si[MAXT];
@@ -267,10 +305,10 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
 #pragma unroll 1
         for (int c = 0;; ++c) {
             const int s = c % NS, fb = c & 1;
-            mbar_wait(&raw_full[s], (c / NS) & 1);
+            mbar_wait_ws(&raw_full[s], (c / NS) & 1);
             const ChunkDesc d = cdesc[s];
             if (!d.valid) break;
-            mbar_wait(&f_free[fb], ((c >> 1) & 1) ^ 1);         // the MMAs that read this tile buffer two chunks ago are done
+            mbar_wait_ws(&f_free[fb], ((c >> 1) & 1) ^ 1);         // the MMAs that read this tile buffer two chunks ago are done
             const unsigned char* stg = stage_ptr(s);
             const float* xs = reinterpret_cast<const float*>(stg + L.o_xs);
             const float* shs = reinterpret_cast<const float*>(stg + L.o_shs);
@@ -316,7 +354,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
 #pragma unroll 1
         for (int c = 0;; ++c) {
             const int s = c % NS, b = c & 1;
-            mbar_wait(&raw_full[s], (c / NS) & 1);
+            mbar_wait_ws(&raw_full[s], (c / NS) & 1);
             const ChunkDesc d = cdesc[s];
             if (!d.valid) {
                 // end of work: hand the sentinel to the epilogue warps through the next accumulator's barrier
@@ -324,7 +362,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     const int seq = d.item_seq + 1;
                     // flow control like a real item: the epilogue must have consumed (hence observed) the previous phase of
                     // this barrier before the sentinel completes the next one
-                    mbar_wait(&acc_empty[seq & 1], ((seq >> 1) & 1) ^ 1);
+                    mbar_wait_ws(&acc_empty[seq & 1], ((seq >> 1) & 1) ^ 1);
                     ItemDesc it; it.ws_off = 0; it.row_stride = 0; it.valid = 0;
                     idesc_ring[seq % NI] = it;
                     asm volatile("fence.acq_rel.cta;" ::: "memory");
@@ -392,7 +430,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 }
                 umma_commit(&hid_bar);
             }
-            mbar_wait(&hid_bar, c & 1);
+            mbar_wait_ws(&hid_bar, c & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t v[16];
             {
@@ -403,7 +441,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             }
-            mbar_wait(&h_free[b], ((c >> 1) & 1) ^ 1);        // the MMAs that read this H~ buffer two chunks ago are done
+            mbar_wait_ws(&h_free[b], ((c >> 1) & 1) ^ 1);        // the MMAs that read this H~ buffer two chunks ago are done
             if (ht < H) {
                 unsigned char* Hhi = smraw + L.hhi[b]; unsigned char* Hlo = smraw + L.hlo[b];
                 const int rbase = (ht >> 3) * SBO + (ht & 7) * 16;
@@ -430,8 +468,8 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             named_bar_sync(1, 32 * H_WARPS);
             if (issuer) {
                 const int acc = d.item_seq & 1;
-                mbar_wait(&f_full[b], (c >> 1) & 1);
-                if (d.flags & 1) mbar_wait(&acc_empty[acc], ((d.item_seq >> 1) & 1) ^ 1);   // the epilogue of item_seq - 2 has drained it
+                mbar_wait_ws(&f_full[b], (c >> 1) & 1);
+                if (d.flags & 1) mbar_wait_ws(&acc_empty[acc], ((d.item_seq >> 1) & 1) ^ 1);   // the epilogue of item_seq - 2 has drained it
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t dacc = tmem_base + (uint32_t)(acc * ACC_COLS);
                 const uint32_t acc0 = (d.flags & 1) ? 0u : 1u;
@@ -451,21 +489,24 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         }
     } else {
         // =============================================================== E: epilogue (TMEM -> registers -> workspace)
-        const int lg = warp & 3;                    // warp 12 is lane group 0
+        const int lg = warp & 3;                    // warps 12..15 and 16..19 are lane groups 0..3
+        const int half = (warp - (F_WARPS + H_WARPS)) >> 2;
         const int j = lg * 32 + lane;
+        const int c_half = ((NRP / 2) + 15) & ~15;
+        const int c_lo = half ? c_half : 0, c_hi = half ? NRP : c_half;
 #pragma unroll 1
         for (int item_seq = 0;; ++item_seq) {
             const int acc = item_seq & 1;
-            mbar_wait(&acc_full[acc], (item_seq >> 1) & 1);
+            mbar_wait_ws(&acc_full[acc], (item_seq >> 1) & 1);
             asm volatile("fence.acq_rel.cta;" ::: "memory");
             const ItemDesc it = idesc_ring[item_seq % NI];
             if (!it.valid) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lg * 32 < H) {                      // warp-uniform: lane groups beyond the hidden width hold nothing
-                float* dst = a.workspace + it.ws_off + j;
-                const int row_stride = it.row_stride;
+                const size_t row_stride = (size_t)it.row_stride;
+                float* dst = a.workspace + it.ws_off + j + (size_t)c_lo * row_stride;
 #pragma unroll 1
-                for (int c0 = 0; c0 < NRP; c0 += 32) {
+                for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * ACC_COLS + c0);
                     asm volatile(
@@ -473,7 +514,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
                           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                         : "r"(taddr));
-                    const bool second = c0 + 16 < NRP;
+                    const bool second = c0 + 16 < c_hi;
                     if (second)
                         asm volatile(
                             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -483,10 +524,14 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (j < H) {
                         const int nr = min(second ? 32 : 16, n_rows - c0);
+                        float* p = dst;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < nr) dst[(size_t)(c0 + i) * row_stride] = __uint_as_float(v[i]);
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < nr) *p = __uint_as_float(v[i]);
+                            p += row_stride;
+                        }
                     }
+                    dst += 32 * row_stride;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

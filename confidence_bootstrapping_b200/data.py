@@ -154,7 +154,8 @@ def _count_h2d(t, device):
 
 def _replicated(vals):
     """True when every tensor of the list has the same content (the N copies of one complex that
-    inference.py / finetune_train.py make with copy.deepcopy share everything but the ligand pose)."""
+    inference.py / finetune_train.py make with copy.deepcopy share everything but the ligand pose).
+    (A thread pool over torch.equal was measured slower than this serial loop: the compare is memory-bound.)"""
     v0 = vals[0]
     if len(vals) < 2 or v0.device.type != "cpu" or v0.numel() == 0:
         return False

@@ -291,7 +291,7 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
             zs.append(z.float().contiguous())
         return zs
 
-    graph, vals, z_static, tor_shape, graph_launches = None, None, None, None, 0
+    graph, vals, z_static, tor_shape, graph_launches, step_table = None, None, None, None, 0, None
     for t_idx in range(inference_steps):
         (t_tr, t_rot, t_tor), coeffs, noisy = scal(t_idx)
         if graph is None:
@@ -316,12 +316,17 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
                         _graph_warned = True
                     graph, use_graph = None, False
             continue
-        # ---- graph replay: refresh the step's scalars and noise, then one launch
-        sig = t_to_sigma(t_tr, t_rot, t_tor)
-        so3_norm = float(so3.score_norm(torch.full((1,), float(sig[1]), dtype=torch.float32))[0])
-        torus_norm = float(torch.tensor(torus.score_norm(np.asarray([sig[2]], dtype=np.float32))).float()[0]) if not no_torsion else 1.0
-        host = torch.tensor([t_tr, t_rot, t_tor, *coeffs, so3_norm, torus_norm], dtype=torch.float32)
-        vals.copy_(host, non_blocking=False)
+        # ---- graph replay: refresh the step's scalars and noise (device-side copies: nothing blocks the host), then one launch
+        if step_table is None:
+            rows = []
+            for k in range(inference_steps):
+                (k_tr, k_rot, k_tor), k_coeffs, _ = scal(k)
+                sig = t_to_sigma(k_tr, k_rot, k_tor)
+                so3_norm = float(so3.score_norm(torch.full((1,), float(sig[1]), dtype=torch.float32))[0])
+                torus_norm = float(torch.tensor(torus.score_norm(np.asarray([sig[2]], dtype=np.float32))).float()[0]) if not no_torsion else 1.0
+                rows.append([k_tr, k_rot, k_tor, *k_coeffs, so3_norm, torus_norm])
+            step_table = torch.tensor(rows, dtype=torch.float32).pin_memory().to(device, non_blocking=True)
+        vals.copy_(step_table[t_idx])
         zs = draw(noisy, tor_shape)
         for zb, z in zip(z_static, zs):
             if (zb is None) != (z is None):
