@@ -7,39 +7,57 @@
 // profiles/r2/k3_ncu_summary_mid.txt), the chunk iterator and the operand gather run ahead on their own warp, and two
 // TMEM accumulators let the epilogue of item i overlap the chunks of item i+1:
 //
-//   warp 20      S  scheduler          : walks the CTA's (node, slot) items; per chunk of 16 edges a descriptor + the 16
-//                                        neighbour indices into stage c % NS (a single warp issuing the whole gather was
-//                                        the bottleneck of the first version: 1300 instructions per chunk at one warp's
-//                                        issue rate, every other role starved -- profiles/r2)
-//   warps 21-24  G  gather             : cp.async the raw operands (x[col], sh, e_attr, P_nbr[col]) of the chunk, four
-//                                        edges per warp, published two chunks later when the copies have landed
 //   warps 0-7    F  f-rows             : CG products of the gathered features -> F^T operand tile (hi/lo), buffer c & 1
-//   warps 8-11   H  hidden layer       : e_attr split -> hidden-layer MMA -> pre-activations back from TMEM -> + node /
-//                                        neighbour projections, ReLU, hi/lo split -> H~ operand tile, buffer c & 1;
-//                                        one thread issues every MMA of the CTA (fixed order => bit-reproducible sums)
-//   warps 12-19  E  epilogue           : finished accumulator TMEM -> registers -> coalesced global stores (workspace);
-//                                        two warps per TMEM lane group, each takes half of the f-row columns
+//   warps 8-15   H  hidden layer       : e_attr split -> E tile; after the hidden-layer MMA: pre-activations back from TMEM
+//                                        (two warps per lane group, 8 edges each) + node / neighbour projections, ReLU,
+//                                        hi/lo split -> H~ operand tile, buffer c & 1
+//   warps 16-19  E  epilogue           : finished accumulator TMEM -> registers -> coalesced global stores (workspace)
+//   warp 20      S  scheduler          : walks the CTA's (node, slot) items; per chunk of 16 edges a descriptor + the 16
+//                                        neighbour indices into stage c % NS (a single warp issuing the whole gather was the
+//                                        bottleneck of the first version: 1300 instructions per chunk at one warp's issue rate)
+//   warps 21-24  G  gather             : cp.async the raw operands (x[col], sh, e_attr, P_nbr[col], P_agg[node]) of the chunk,
+//                                        four edges per warp, published two chunks later when the copies have landed
+//   warp 25      I  MMA issuer         : ONE thread issues every tcgen05.mma of the CTA in a fixed order (bit-reproducible):
+//                                        main(c), then hidden(c+1) right behind it, so the H warps turn the pre-activations of
+//                                        chunk c+1 into its H~ tile while the tensor pipe still runs the rank-16 update of
+//                                        chunk c.  (In v1 hidden unit 0 issued the MMAs: its timeline -- tile production AND
+//                                        the issue back-pressure of the tensor pipe -- was 82 % busy and paced the whole CTA,
+//                                        profiles/r2/phase_ws_v1.log)
 //
 //   barrier           producer -> consumer            count
 //   desc_full[s]      S (descriptor)   -> G           1
-//   raw_full[s]       G (data landed)  -> F, H        4
-//   raw_empty[s]      F, H (stage read) -> S          12 (one lane per warp)
-//   f_full[b]         F (tile written) -> H issuer    8
+//   raw_full[s]       G (data landed)  -> F, H, I     4
+//   raw_empty[s]      F, H, I (stage read) -> S       17 (one lane per warp)
+//   f_full[b]         F (tile written) -> I           8
 //   f_free[b]         tcgen05.commit   -> F           1
+//   e_full            H (E tile)       -> I           8
+//   hid_done          tcgen05.commit   -> H           1
+//   h_full[b]         H (H~ tile)      -> I           8
 //   h_free[b]         tcgen05.commit   -> H           1
-//   hid_bar           tcgen05.commit   -> H           1
 //   acc_full[a]       tcgen05.commit   -> E           1   (or a plain arrive carrying the end-of-work sentinel)
-//   acc_empty[a]      E (TMEM read)    -> H issuer    8
+//   acc_empty[a]      E (TMEM read)    -> I           4
 //
 // TMEM (512 columns, one CTA per SM): accumulator a at column 240 a, hidden pre-activations at 480.
 // Every wait is a bounded spin that traps instead of hanging the GPU.
 
 namespace ws {
 
+#ifdef CB_PHASE_TIMING
+#define WS_T0() long long wph[12] = {0,0,0,0,0,0,0,0,0,0,0,0}, wt = clock64(); long long wcount = 0
+#define WS_MARK(k) do { const long long t_ = clock64(); wph[k] += t_ - wt; wt = t_; } while (0)
+#define WS_FLUSH(row) do { for (int k_ = 0; k_ < 12; ++k_) atomicAdd(&cb_dbg_phase[row][k_], (unsigned long long)wph[k_]); } while (0)
+#else
+#define WS_T0() do { } while (0)
+#define WS_MARK(k) do { } while (0)
+#define WS_FLUSH(row) do { } while (0)
+#endif
+
 constexpr int NS = 4;                 // raw-operand stages the scheduler may run ahead
 constexpr int NI = 8;                 // item-descriptor ring (>= NS + 2 items can be open between S and E)
-constexpr int F_WARPS = 8, H_WARPS = 4, E_WARPS = 8, G_WARPS = 4;
-constexpr int THREADS_WS = 32 * (F_WARPS + H_WARPS + E_WARPS + 1 + G_WARPS);
+constexpr int F_WARPS = 8, H_WARPS = 8, E_WARPS = 4, G_WARPS = 4;
+// warp order: F | H | E | S | G... | I
+constexpr int W_S = F_WARPS + H_WARPS + E_WARPS, W_G0 = W_S + 1, W_I = W_G0 + G_WARPS;
+constexpr int THREADS_WS = 32 * (W_I + 1);
 constexpr int ACC_COLS = 240;
 constexpr int TMEM_COLS_WS = 512;
 
@@ -48,7 +66,7 @@ struct ItemDesc { unsigned long long ws_off; int row_stride, valid; };
 
 struct LayoutWS {
     int fhi[2], flo[2], hhi[2], hlo[2], ehi, elo, w1hi, w1lo, raw, rows, terms, cdesc, idesc, total;   // byte offsets
-    int raw_stage, o_xs, o_shs, o_es, o_ps;     // bytes per raw stage and offsets inside it
+    int raw_stage, o_xs, o_shs, o_es, o_ps, o_pa;     // bytes per raw stage and offsets inside it
     int dxp, sbow, f_groups;
 };
 
@@ -69,7 +87,8 @@ __host__ __device__ inline LayoutWS make_layout_ws(int n_rows, int n_terms, int 
     L.o_shs = L.o_xs + al(KC * L.dxp * 4, 16);
     L.o_es = L.o_shs + al(KC * S * 4, 16);
     L.o_ps = L.o_es + al(KC * ne * 4, 16);
-    L.raw_stage = L.o_ps + al(KC * H * 4, 16);
+    L.o_pa = L.o_ps + al(KC * H * 4, 16);          // P_agg[node] row of the item (first chunk of an item only)
+    L.raw_stage = L.o_pa + al(H * 4, 16);
     L.raw = o;  o += NS * L.raw_stage;
     L.rows = o; o += al(n_rows * 32, 16);
     L.terms = o; o += al(n_terms * 8, 16);
@@ -120,7 +139,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     ChunkDesc* cdesc = reinterpret_cast<ChunkDesc*>(smraw + L.cdesc);
     ItemDesc* idesc_ring = reinterpret_cast<ItemDesc*>(smraw + L.idesc);
     __shared__ SlotTable st;
-    __shared__ __align__(8) uint64_t desc_full[NS], raw_full[NS], raw_empty[NS], f_full[2], f_free[2], h_free[2], hid_bar, acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t desc_full[NS], raw_full[NS], raw_empty[NS], f_full[2], f_free[2], h_full[2], h_free[2], e_full, hid_done, acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -128,12 +147,12 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     // ---- once per CTA
     if (tid == 0) {
         build_slots(a, st);
-        for (int s = 0; s < NS; ++s) { mbar_init(&desc_full[s], 1); mbar_init(&raw_full[s], G_WARPS); mbar_init(&raw_empty[s], F_WARPS + H_WARPS); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&desc_full[s], 1); mbar_init(&raw_full[s], G_WARPS); mbar_init(&raw_empty[s], F_WARPS + H_WARPS + 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&f_full[b], F_WARPS); mbar_init(&f_free[b], 1); mbar_init(&h_free[b], 1);
+            mbar_init(&f_full[b], F_WARPS); mbar_init(&f_free[b], 1); mbar_init(&h_full[b], H_WARPS); mbar_init(&h_free[b], 1);
             mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], E_WARPS);
         }
-        mbar_init(&hid_bar, 1);
+        mbar_init(&e_full, H_WARPS); mbar_init(&hid_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -163,7 +182,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
 
     auto stage_ptr = [&](int s) { return smraw + L.raw + s * L.raw_stage; };
 
-    if (warp == F_WARPS + H_WARPS + E_WARPS) {
+    if (warp == W_S) {
         // =============================================================== S: scheduler (one warp, warp-uniform control)
         auto seg_range = [&](int seg, int node, int& e0, int& e1) { seg_edges(a.segs[seg], node, e0, e1); };
         int item = blockIdx.x, q = 0, item_seq = -1;
@@ -235,9 +254,9 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             }
             if (!done) item += (int)gridDim.x;
         }
-    } else if (warp > F_WARPS + H_WARPS + E_WARPS) {
+    } else if (warp >= W_G0 && warp < W_I) {
         // =============================================================== G: gather warps (edges g, g+4, g+8, g+12 of every chunk)
-        const int g = warp - (F_WARPS + H_WARPS + E_WARPS + 1);
+        const int g = warp - W_G0;
         int pending = 0;
         int c = 0;
 #pragma unroll 1
@@ -265,6 +284,15 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                         const float* pr = sg.P_nbr + (size_t)col * sg.ldp_nbr;
 #pragma unroll 1
                         for (int k = lane; k < H / 4; k += 32) cp_async_bytes16(ps + e * H + 4 * k, pr + 4 * k);
+                    }
+                }
+                if (g == G_WARPS - 1 && (d.flags & 1)) {      // per-item constant of the hidden layer: the aggregation node's projection row
+                    const cb_tp_segment& s0 = a.segs[st.first_seg[d.q]];
+                    if (s0.P_agg) {
+                        float* pa = reinterpret_cast<float*>(stg + L.o_pa);
+                        const float* pr = s0.P_agg + (size_t)d.node * s0.ldp_agg;
+#pragma unroll 1
+                        for (int k = lane; k < H / 4; k += 32) cp_async_bytes16(pa + 4 * k, pr + 4 * k);
                     }
                 }
 #pragma unroll 1
@@ -333,52 +361,34 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             }
         }
     } else if (warp < F_WARPS + H_WARPS) {
-        // =============================================================== H: hidden layer, H~ tiles, MMA issue
-        const int ht = tid - 32 * F_WARPS;          // 0..127 = hidden unit = TMEM lane
-        const int lg = warp & 3;                    // == ht >> 5 (warp 8 is lane group 0)
-        const bool issuer = ht == 0;
+        // =============================================================== H: E tile, then pre-activations -> H~ tile
+        const int hw = warp - F_WARPS;              // 0..7
+        const int lg = warp & 3;                    // TMEM lane group (warp 8 is lane group 0)
+        const int eh = hw >> 2;                     // which 8 of the chunk's 16 edges
+        const int q_unit = lg * 32 + lane;          // hidden unit = TMEM lane
+        const int ht = tid - 32 * F_WARPS;          // 0..255 within the role
         unsigned char* Ehi = smraw + L.ehi; unsigned char* Elo = smraw + L.elo;
         unsigned char* W1hi = smraw + L.w1hi; unsigned char* W1lo = smraw + L.w1lo;
-        const uint64_t d_w1hi = make_desc_sbo(smem_u32(W1hi), SBOW), d_w1lo = make_desc_sbo(smem_u32(W1lo), SBOW);
-        const uint64_t d_ehi = make_desc_sbo(smem_u32(Ehi), SBOW), d_elo = make_desc_sbo(smem_u32(Elo), SBOW);
-        uint64_t d_fhi[2], d_flo[2], d_hhi[2], d_hlo[2];
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            d_fhi[b] = make_desc(smem_u32(smraw + L.fhi[b])); d_flo[b] = make_desc(smem_u32(smraw + L.flo[b]));
-            d_hhi[b] = make_desc(smem_u32(smraw + L.hhi[b])); d_hlo[b] = make_desc(smem_u32(smraw + L.hlo[b]));
-        }
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NRP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc_h = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         int staged_slot = -1, hb_q = -1, hb_graph = -1;
         float hb_const = 0.0f, hb = 0.0f;
+        WS_T0();
 #pragma unroll 1
         for (int c = 0;; ++c) {
             const int s = c % NS, b = c & 1;
             mbar_wait_ws(&raw_full[s], (c / NS) & 1);
+            WS_MARK(0);
             const ChunkDesc d = cdesc[s];
-            if (!d.valid) {
-                // end of work: hand the sentinel to the epilogue warps through the next accumulator's barrier
-                if (issuer) {
-                    const int seq = d.item_seq + 1;
-                    // flow control like a real item: the epilogue must have consumed (hence observed) the previous phase of
-                    // this barrier before the sentinel completes the next one
-                    mbar_wait_ws(&acc_empty[seq & 1], ((seq >> 1) & 1) ^ 1);
-                    ItemDesc it; it.ws_off = 0; it.row_stride = 0; it.valid = 0;
-                    idesc_ring[seq % NI] = it;
-                    asm volatile("fence.acq_rel.cta;" ::: "memory");
-                    mbar_arrive(&acc_full[seq & 1]);
-                }
-                break;
-            }
+            if (!d.valid) break;
             const cb_tp_segment& sg = a.segs[d.seg];
             const unsigned char* stg = stage_ptr(s);
             const float* es = reinterpret_cast<const float*>(stg + L.o_es);
             const float* Ps = reinterpret_cast<const float*>(stg + L.o_ps);
             const int n = d.n, ksteps = (n + 7) >> 3;
             if (d.flags & 1) {
-                // ---- per-item constants: first Linear's edge-embedding slice as operand tiles (on slot change), bias + node projection
+                // ---- per-item constants: first Linear's edge-embedding slice as operand tiles (on slot change), bias + node projection.
+                // No hidden-layer MMA is in flight here: the role waited for hid_done of the previous chunk.
                 const cb_tp_segment& s0 = a.segs[st.first_seg[d.q]];
-                if (staged_slot != d.q) {           // block-uniform within the role: no hidden-layer MMA is in flight here
+                if (staged_slot != d.q) {
 #pragma unroll 1
                     for (int i = ht; i < H * (ne / 4); i += 32 * H_WARPS) {
                         const int qq = i / (ne / 4), c4 = i - qq * (ne / 4);
@@ -391,18 +401,18 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     }
                     staged_slot = d.q;
                 }
-                if (ht < H) {
-                    const int graph = a.agg_graph ? __ldg(a.agg_graph + d.node) : 0;
+                if (q_unit < H) {
+                    const int graph = (s0.e_post && a.agg_graph) ? __ldg(a.agg_graph + d.node) : 0;
                     if (hb_q != d.q || (s0.e_post && hb_graph != graph)) {
-                        float v = __ldg(s0.b1 + ht);
+                        float v = __ldg(s0.b1 + q_unit);
                         if (s0.e_post) {
                             const float* ep = s0.e_post + (size_t)graph * ne;
 #pragma unroll 4
-                            for (int k = 0; k < ne; ++k) v = fmaf(__ldg(s0.W1e + (size_t)ht * s0.ldw1 + k), __ldg(ep + k), v);
+                            for (int k = 0; k < ne; ++k) v = fmaf(__ldg(s0.W1e + (size_t)q_unit * s0.ldw1 + k), __ldg(ep + k), v);
                         }
                         hb_const = v; hb_q = d.q; hb_graph = graph;
                     }
-                    hb = hb_const + (s0.P_agg ? __ldg(s0.P_agg + (size_t)d.node * s0.ldp_agg + ht) : 0.0f);
+                    hb = hb_const + (s0.P_agg ? reinterpret_cast<const float*>(stg + L.o_pa)[q_unit] : 0.0f);   // row gathered with the chunk
                 }
             }
             // ---- edge-embedding rows of the chunk as hi/lo B tiles of the hidden-layer MMA
@@ -417,42 +427,34 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 *reinterpret_cast<float4*>(Elo + off) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            named_bar_sync(1, 32 * H_WARPS);
-            if (issuer) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint64_t dwh = d_w1hi, dwl = d_w1lo, deh = d_ehi, del = d_elo;
-#pragma unroll 2
-                for (int ks = 0; ks < ne / 8; ++ks) {
-                    mma_tf32(tmem_hid, dwh, deh, idesc_h, ks > 0 ? 1u : 0u);
-                    mma_tf32(tmem_hid, dwh, del, idesc_h, 1u);
-                    mma_tf32(tmem_hid, dwl, deh, idesc_h, 1u);
-                    dwh += (2 * LBO) >> 4; dwl += (2 * LBO) >> 4; deh += (2 * LBO) >> 4; del += (2 * LBO) >> 4;
-                }
-                umma_commit(&hid_bar);
-            }
-            mbar_wait_ws(&hid_bar, c & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&e_full);
+            WS_MARK(1);
+            mbar_wait_ws(&hid_done, c & 1);
+            WS_MARK(4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t v[16];
-            {
-                const uint32_t taddr = tmem_hid + ((uint32_t)(lg * 32) << 16);
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            uint32_t v[8];
+            if (eh < ksteps) {       // warp-uniform
+                const uint32_t taddr = tmem_hid + ((uint32_t)(lg * 32) << 16) + (uint32_t)(8 * eh);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             }
+            WS_MARK(5);
             mbar_wait_ws(&h_free[b], ((c >> 1) & 1) ^ 1);        // the MMAs that read this H~ buffer two chunks ago are done
-            if (ht < H) {
+            WS_MARK(6);
+            if (eh < ksteps && q_unit < H) {
                 unsigned char* Hhi = smraw + L.hhi[b]; unsigned char* Hlo = smraw + L.hlo[b];
-                const int rbase = (ht >> 3) * SBO + (ht & 7) * 16;
+                const int rbase = (q_unit >> 3) * SBO + (q_unit & 7) * 16 + 2 * eh * LBO;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 2; ++g) {
                     float h[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int e = 4 * g + j;
-                        float pre = __uint_as_float(v[e]) + hb;
-                        if (sg.P_nbr) pre += Ps[e * H + ht];
+                        const int e = 8 * eh + 4 * g + j;
+                        float pre = __uint_as_float(v[4 * g + j]) + hb;
+                        if (sg.P_nbr) pre += Ps[e * H + q_unit];
                         h[j] = e < n ? fmaxf(pre, 0.0f) : 0.0f;
                     }
                     float4 hi, lo;
@@ -464,36 +466,90 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[s]);
-            named_bar_sync(1, 32 * H_WARPS);
-            if (issuer) {
-                const int acc = d.item_seq & 1;
+            if (lane == 0) { mbar_arrive(&h_full[b]); mbar_arrive(&raw_empty[s]); }
+            WS_MARK(7);
+        }
+        if (ht == 0) WS_FLUSH(0);
+        if (ht == 255) WS_FLUSH(1);
+    } else if (warp == W_I) {
+        // =============================================================== I: the CTA's MMA issuer (one thread)
+        if (lane == 0) {
+            const uint64_t d_w1hi = make_desc_sbo(smem_u32(smraw + L.w1hi), SBOW), d_w1lo = make_desc_sbo(smem_u32(smraw + L.w1lo), SBOW);
+            const uint64_t d_ehi = make_desc_sbo(smem_u32(smraw + L.ehi), SBOW), d_elo = make_desc_sbo(smem_u32(smraw + L.elo), SBOW);
+            const uint64_t d_f0h = make_desc(smem_u32(smraw + L.fhi[0])), d_f0l = make_desc(smem_u32(smraw + L.flo[0]));
+            const uint64_t d_f1h = make_desc(smem_u32(smraw + L.fhi[1])), d_f1l = make_desc(smem_u32(smraw + L.flo[1]));
+            const uint64_t d_h0h = make_desc(smem_u32(smraw + L.hhi[0])), d_h0l = make_desc(smem_u32(smraw + L.hlo[0]));
+            const uint64_t d_h1h = make_desc(smem_u32(smraw + L.hhi[1])), d_h1l = make_desc(smem_u32(smraw + L.hlo[1]));
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NRP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_h = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            auto issue_hidden = [&](int c) {      // pre[q][e] = sum_k W1e[q][k] e_attr[e][k] of chunk c (E tile published by the H warps)
+                mbar_wait_ws(&e_full, c & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint64_t dwh = d_w1hi, dwl = d_w1lo, deh = d_ehi, del = d_elo;
+#pragma unroll 2
+                for (int ks = 0; ks < ne / 8; ++ks) {
+                    mma_tf32(tmem_hid, dwh, deh, idesc_h, ks > 0 ? 1u : 0u);
+                    mma_tf32(tmem_hid, dwh, del, idesc_h, 1u);
+                    mma_tf32(tmem_hid, dwl, deh, idesc_h, 1u);
+                    dwh += (2 * LBO) >> 4; dwl += (2 * LBO) >> 4; deh += (2 * LBO) >> 4; del += (2 * LBO) >> 4;
+                }
+                umma_commit(&hid_done);
+            };
+            // chunk descriptors are read one chunk ahead (the stage is released to the scheduler right after the read)
+            mbar_wait_ws(&raw_full[0], 0);
+            ChunkDesc d = cdesc[0];
+            mbar_arrive(&raw_empty[0]);
+            if (d.valid) issue_hidden(0);
+#pragma unroll 1
+            for (int c = 0;; ++c) {
+                if (!d.valid) {
+                    // end of work: hand the sentinel to the epilogue warps through the next accumulator's barrier, with the flow
+                    // control of a real item (the epilogue must have consumed the previous phase of that barrier)
+                    const int seq = d.item_seq + 1;
+                    mbar_wait_ws(&acc_empty[seq & 1], ((seq >> 1) & 1) ^ 1);
+                    ItemDesc it; it.ws_off = 0; it.row_stride = 0; it.valid = 0;
+                    idesc_ring[seq % NI] = it;
+                    asm volatile("fence.acq_rel.cta;" ::: "memory");
+                    mbar_arrive(&acc_full[seq & 1]);
+                    break;
+                }
+                const int b = c & 1;
+                const int s1 = (c + 1) % NS;
+                mbar_wait_ws(&raw_full[s1], ((c + 1) / NS) & 1);
+                const ChunkDesc d1 = cdesc[s1];
+                mbar_arrive(&raw_empty[s1]);
+                // main(c): needs H~(c) and F^T(c); a new item also needs its accumulator drained by the epilogue
+                mbar_wait_ws(&h_full[b], (c >> 1) & 1);
                 mbar_wait_ws(&f_full[b], (c >> 1) & 1);
-                if (d.flags & 1) mbar_wait_ws(&acc_empty[acc], ((d.item_seq >> 1) & 1) ^ 1);   // the epilogue of item_seq - 2 has drained it
+                const int acc = d.item_seq & 1;
+                if (d.flags & 1) mbar_wait_ws(&acc_empty[acc], ((d.item_seq >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t dacc = tmem_base + (uint32_t)(acc * ACC_COLS);
                 const uint32_t acc0 = (d.flags & 1) ? 0u : 1u;
-                mma_tf32(dacc, d_hhi[b], d_fhi[b], idesc, acc0);
-                mma_tf32(dacc, d_hhi[b], d_flo[b], idesc, 1u);
-                mma_tf32(dacc, d_hlo[b], d_fhi[b], idesc, 1u);
-                if (ksteps > 1) {
+                const uint64_t fh = b ? d_f1h : d_f0h, fl = b ? d_f1l : d_f0l, hh = b ? d_h1h : d_h0h, hl = b ? d_h1l : d_h0l;
+                mma_tf32(dacc, hh, fh, idesc, acc0);
+                mma_tf32(dacc, hh, fl, idesc, 1u);
+                mma_tf32(dacc, hl, fh, idesc, 1u);
+                if (((d.n + 7) >> 3) > 1) {
                     const uint64_t ks = (uint64_t)((2 * LBO) >> 4);
-                    mma_tf32(dacc, d_hhi[b] + ks, d_fhi[b] + ks, idesc, 1u);
-                    mma_tf32(dacc, d_hhi[b] + ks, d_flo[b] + ks, idesc, 1u);
-                    mma_tf32(dacc, d_hlo[b] + ks, d_fhi[b] + ks, idesc, 1u);
+                    mma_tf32(dacc, hh + ks, fh + ks, idesc, 1u);
+                    mma_tf32(dacc, hh + ks, fl + ks, idesc, 1u);
+                    mma_tf32(dacc, hl + ks, fh + ks, idesc, 1u);
                 }
                 umma_commit(&f_free[b]);
                 umma_commit(&h_free[b]);
                 if (d.flags & 2) umma_commit(&acc_full[acc]);
+                // hidden(c+1) right behind main(c): its E tile is published by the H warps after they finished H~(c), and they
+                // read the pre-activations back while the tensor pipe is still busy with main(c)
+                if (d1.valid) issue_hidden(c + 1);
+                d = d1;
             }
         }
     } else {
         // =============================================================== E: epilogue (TMEM -> registers -> workspace)
-        const int lg = warp & 3;                    // warps 12..15 and 16..19 are lane groups 0..3
-        const int half = (warp - (F_WARPS + H_WARPS)) >> 2;
+        const int lg = warp & 3;                    // warps 16..19 are lane groups 0..3
         const int j = lg * 32 + lane;
-        const int c_half = ((NRP / 2) + 15) & ~15;
-        const int c_lo = half ? c_half : 0, c_hi = half ? NRP : c_half;
+        const int c_lo = 0, c_hi = NRP;        // one warp per lane group: all f-row columns
 #pragma unroll 1
         for (int item_seq = 0;; ++item_seq) {
             const int acc = item_seq & 1;
@@ -527,7 +583,11 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                         float* p = dst;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
+#ifndef CB_WS_NO_STORE
                             if (i < nr) *p = __uint_as_float(v[i]);
+#else
+                            if (i < nr && v[i] == 0x7fc12345u) *p = 1.0f;     // experiment: keep the TMEM reads, drop the stores
+#endif
                             p += row_stride;
                         }
                     }
