@@ -17,27 +17,28 @@
 //                                        bottleneck of the first version: 1300 instructions per chunk at one warp's issue rate)
 //   warps 21-24  G  gather             : cp.async the raw operands (x[col], sh, e_attr, P_nbr[col], P_agg[node]) of the chunk,
 //                                        four edges per warp, published two chunks later when the copies have landed
-//   warp 25      I  MMA issuer         : ONE thread issues every tcgen05.mma of the CTA in a fixed order (bit-reproducible):
-//                                        main(c), then hidden(c+1) right behind it, so the H warps turn the pre-activations of
-//                                        chunk c+1 into its H~ tile while the tensor pipe still runs the rank-16 update of
-//                                        chunk c.  (In v1 hidden unit 0 issued the MMAs: its timeline -- tile production AND
+//   warp 25      I  MMA issuer         : ONE thread issues every tcgen05.mma of the CTA.  The H warps publish the E tile of
+//                                        chunk c+1 BEFORE they await the pre-activations of chunk c, so the tensor pipe runs
+//                                        hidden(c+1) ahead of main(c) and the H~ tile of chunk c+1 is produced while main(c)
+//                                        executes (v2 served hidden(c+1) after main(c): the H warps then waited 36 % of their
+//                                        time for pre-activations queued behind a 720-cycle rank-16 update).  (In v1 hidden unit 0 issued the MMAs: its timeline -- tile production AND
 //                                        the issue back-pressure of the tensor pipe -- was 82 % busy and paced the whole CTA,
 //                                        profiles/r2/phase_ws_v1.log)
 //
 //   barrier           producer -> consumer            count
 //   desc_full[s]      S (descriptor)   -> G           1
-//   raw_full[s]       G (data landed)  -> F, H, I     4
-//   raw_empty[s]      F, H, I (stage read) -> S       17 (one lane per warp)
+//   raw_full[s]       G (data landed)  -> F, H        4
+//   raw_empty[s]      F, H (stage read) -> S          16 (one lane per warp)
 //   f_full[b]         F (tile written) -> I           8
 //   f_free[b]         tcgen05.commit   -> F           1
-//   e_full            H (E tile)       -> I           8
-//   hid_done          tcgen05.commit   -> H           1
+//   e_full[b]         H (E tile)       -> I           8   (ictl_e[b] = 0 marks the end of the work)
+//   hid_done[b]       tcgen05.commit   -> H           1
 //   h_full[b]         H (H~ tile)      -> I           8
 //   h_free[b]         tcgen05.commit   -> H           1
 //   acc_full[a]       tcgen05.commit   -> E           1   (or a plain arrive carrying the end-of-work sentinel)
 //   acc_empty[a]      E (TMEM read)    -> I           4
 //
-// TMEM (512 columns, one CTA per SM): accumulator a at column 240 a, hidden pre-activations at 480.
+// TMEM (512 columns, one CTA per SM): accumulator a at column 240 a, hidden pre-activations of chunk k at 480 + 16 (k & 1).
 // Every wait is a bounded spin that traps instead of hanging the GPU.
 
 namespace ws {
@@ -52,7 +53,8 @@ namespace ws {
 #define WS_FLUSH(row) do { } while (0)
 #endif
 
-constexpr int NS = 4;                 // raw-operand stages the scheduler may run ahead
+constexpr int NS = 6;                 // raw-operand stages the scheduler may run ahead
+constexpr int LAG = 2;                // a chunk's gather is published LAG chunks after it was issued (its copies have landed)
 constexpr int NI = 8;                 // item-descriptor ring (>= NS + 2 items can be open between S and E)
 constexpr int F_WARPS = 8, H_WARPS = 8, E_WARPS = 4, G_WARPS = 4;
 // warp order: F | H | E | S | G... | I
@@ -65,7 +67,7 @@ struct ChunkDesc { int valid, seg, n, flags, item_seq, node, q, pad; };     // f
 struct ItemDesc { unsigned long long ws_off; int row_stride, valid; };
 
 struct LayoutWS {
-    int fhi[2], flo[2], hhi[2], hlo[2], ehi, elo, w1hi, w1lo, raw, rows, terms, cdesc, idesc, total;   // byte offsets
+    int fhi[2], flo[2], hhi[2], hlo[2], ehi[2], elo[2], w1hi, w1lo, raw, rows, terms, cdesc, idesc, total;   // byte offsets
     int raw_stage, o_xs, o_shs, o_es, o_ps, o_pa;     // bytes per raw stage and offsets inside it
     int dxp, sbow, f_groups;
 };
@@ -79,8 +81,7 @@ __host__ __device__ inline LayoutWS make_layout_ws(int n_rows, int n_terms, int 
     int o = 0;
     for (int b = 0; b < 2; ++b) { L.fhi[b] = o; o += L.f_groups * SBO; L.flo[b] = o; o += L.f_groups * SBO; }
     for (int b = 0; b < 2; ++b) { L.hhi[b] = o; o += 16 * SBO; L.hlo[b] = o; o += 16 * SBO; }
-    L.ehi = o;  o += (KC / 8) * L.sbow;
-    L.elo = o;  o += (KC / 8) * L.sbow;
+    for (int b = 0; b < 2; ++b) { L.ehi[b] = o; o += (KC / 8) * L.sbow; L.elo[b] = o; o += (KC / 8) * L.sbow; }
     L.w1hi = o; o += 16 * L.sbow;          // full 128 rows: rows >= H stay zero (nothing may follow that a stale read could hit)
     L.w1lo = o; o += 16 * L.sbow;
     L.o_xs = 64;                           // the stage starts with the chunk's 16 neighbour indices
@@ -99,6 +100,7 @@ __host__ __device__ inline LayoutWS make_layout_ws(int n_rows, int n_terms, int 
 }
 
 // bounded wait: a lost arrival traps after ~1.5 s of spinning instead of hanging the GPU (the kernel itself runs ~1 ms)
+// (An out-of-line copy and a sleep between polls were both measured slower.)
 __device__ __forceinline__ void mbar_wait_ws(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     const long long t0 = clock64();
@@ -112,6 +114,16 @@ __device__ __forceinline__ void mbar_wait_ws(uint64_t* bar, uint32_t parity) {
         if (ok) return;
         if ((spin & 255u) == 255u && clock64() - t0 > 3000000000ll) __trap();
     }
+}
+
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -139,7 +151,9 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     ChunkDesc* cdesc = reinterpret_cast<ChunkDesc*>(smraw + L.cdesc);
     ItemDesc* idesc_ring = reinterpret_cast<ItemDesc*>(smraw + L.idesc);
     __shared__ SlotTable st;
-    __shared__ __align__(8) uint64_t desc_full[NS], raw_full[NS], raw_empty[NS], f_full[2], f_free[2], h_full[2], h_free[2], e_full, hid_done, acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t desc_full[NS], raw_full[NS], raw_empty[NS], f_full[2], f_free[2], h_full[2], h_free[2], e_full[2], hid_done[2], acc_full[2], acc_empty[2];
+    __shared__ int ictl_e[2];                    // H -> I: does chunk k (buffer k & 1) exist?
+    __shared__ int4 ictl_m[2];                   // H -> I: (flags, item_seq, n) of the chunk whose H~ tile sits in buffer k & 1
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -147,12 +161,12 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
     // ---- once per CTA
     if (tid == 0) {
         build_slots(a, st);
-        for (int s = 0; s < NS; ++s) { mbar_init(&desc_full[s], 1); mbar_init(&raw_full[s], G_WARPS); mbar_init(&raw_empty[s], F_WARPS + H_WARPS + 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&desc_full[s], 1); mbar_init(&raw_full[s], G_WARPS); mbar_init(&raw_empty[s], F_WARPS + H_WARPS); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&f_full[b], F_WARPS); mbar_init(&f_free[b], 1); mbar_init(&h_full[b], H_WARPS); mbar_init(&h_free[b], 1);
+            mbar_init(&f_full[b], F_WARPS); mbar_init(&f_free[b], 1); mbar_init(&h_full[b], H_WARPS); mbar_init(&h_free[b], 1); mbar_init(&e_full[b], H_WARPS); mbar_init(&hid_done[b], 1);
             mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], E_WARPS);
         }
-        mbar_init(&e_full, H_WARPS); mbar_init(&hid_done, 1);
+
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -302,11 +316,11 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             ++pending;
-            // publish the chunk issued NS-2 iterations ago: this warp's copies for it have landed
-            if (pending > NS - 2) {
-                asm volatile("cp.async.wait_group %0;\n" ::"n"(NS - 2) : "memory");
+            // publish the chunk issued LAG iterations ago: this warp's copies for it have landed
+            if (pending > LAG) {
+                asm volatile("cp.async.wait_group %0;\n" ::"n"(LAG) : "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&raw_full[(c - (NS - 2)) % NS]);
+                if (lane == 0) mbar_arrive(&raw_full[(c - LAG) % NS]);
                 --pending;
             }
             if (!d.valid) break;
@@ -361,34 +375,25 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             }
         }
     } else if (warp < F_WARPS + H_WARPS) {
-        // =============================================================== H: E tile, then pre-activations -> H~ tile
+        // =============================================================== H: E tile (one chunk ahead), then pre-activations -> H~ tile
         const int hw = warp - F_WARPS;              // 0..7
         const int lg = warp & 3;                    // TMEM lane group (warp 8 is lane group 0)
         const int eh = hw >> 2;                     // which 8 of the chunk's 16 edges
         const int q_unit = lg * 32 + lane;          // hidden unit = TMEM lane
         const int ht = tid - 32 * F_WARPS;          // 0..255 within the role
-        unsigned char* Ehi = smraw + L.ehi; unsigned char* Elo = smraw + L.elo;
         unsigned char* W1hi = smraw + L.w1hi; unsigned char* W1lo = smraw + L.w1lo;
         int staged_slot = -1, hb_q = -1, hb_graph = -1;
-        float hb_const = 0.0f, hb = 0.0f;
+        float hb_const = 0.0f;
         WS_T0();
-#pragma unroll 1
-        for (int c = 0;; ++c) {
-            const int s = c % NS, b = c & 1;
-            mbar_wait_ws(&raw_full[s], (c / NS) & 1);
-            WS_MARK(0);
-            const ChunkDesc d = cdesc[s];
-            if (!d.valid) break;
-            const cb_tp_segment& sg = a.segs[d.seg];
+        // E-phase of chunk k (descriptor d, stage s): per-item constants when the chunk opens an item, then the chunk's
+        // edge-embedding rows as hi/lo B tiles of the hidden-layer MMA (buffer k & 1).  Returns the item's hidden-layer bias.
+        auto e_phase = [&](int k, const ChunkDesc& d, int s, float hb_prev) -> float {
             const unsigned char* stg = stage_ptr(s);
             const float* es = reinterpret_cast<const float*>(stg + L.o_es);
-            const float* Ps = reinterpret_cast<const float*>(stg + L.o_ps);
-            const int n = d.n, ksteps = (n + 7) >> 3;
+            float hb = hb_prev;
             if (d.flags & 1) {
-                // ---- per-item constants: first Linear's edge-embedding slice as operand tiles (on slot change), bias + node projection.
-                // No hidden-layer MMA is in flight here: the role waited for hid_done of the previous chunk.
                 const cb_tp_segment& s0 = a.segs[st.first_seg[d.q]];
-                if (staged_slot != d.q) {
+                if (staged_slot != d.q) {       // only reached when no hidden-layer MMA is in flight (see the loop below)
 #pragma unroll 1
                     for (int i = ht; i < H * (ne / 4); i += 32 * H_WARPS) {
                         const int qq = i / (ne / 4), c4 = i - qq * (ne / 4);
@@ -408,66 +413,105 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                         if (s0.e_post) {
                             const float* ep = s0.e_post + (size_t)graph * ne;
 #pragma unroll 4
-                            for (int k = 0; k < ne; ++k) v = fmaf(__ldg(s0.W1e + (size_t)q_unit * s0.ldw1 + k), __ldg(ep + k), v);
+                            for (int kk = 0; kk < ne; ++kk) v = fmaf(__ldg(s0.W1e + (size_t)q_unit * s0.ldw1 + kk), __ldg(ep + kk), v);
                         }
                         hb_const = v; hb_q = d.q; hb_graph = graph;
                     }
                     hb = hb_const + (s0.P_agg ? reinterpret_cast<const float*>(stg + L.o_pa)[q_unit] : 0.0f);   // row gathered with the chunk
                 }
             }
-            // ---- edge-embedding rows of the chunk as hi/lo B tiles of the hidden-layer MMA
+            unsigned char* Ehi = smraw + L.ehi[k & 1]; unsigned char* Elo = smraw + L.elo[k & 1];
 #pragma unroll 1
             for (int i = ht; i < KC * (ne / 4); i += 32 * H_WARPS) {
                 const int e = i / (ne / 4), c4 = i - e * (ne / 4);
-                const float4 v = *reinterpret_cast<const float4*>(es + e * ne + 4 * c4);     // rows >= n hold stale data: discarded below
+                const float4 v = *reinterpret_cast<const float4*>(es + e * ne + 4 * c4);     // rows >= n hold stale data: discarded later
                 float4 hi, lo;
                 split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
                 const int off = (e >> 3) * SBOW + c4 * LBO + (e & 7) * 16;
                 *reinterpret_cast<float4*>(Ehi + off) = hi;
                 *reinterpret_cast<float4*>(Elo + off) = lo;
             }
+            if (ht == 0) ictl_e[k & 1] = 1;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&e_full);
-            WS_MARK(1);
-            mbar_wait_ws(&hid_done, c & 1);
-            WS_MARK(4);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t v[8];
-            if (eh < ksteps) {       // warp-uniform
-                const uint32_t taddr = tmem_hid + ((uint32_t)(lg * 32) << 16) + (uint32_t)(8 * eh);
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                             : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            }
-            WS_MARK(5);
-            mbar_wait_ws(&h_free[b], ((c >> 1) & 1) ^ 1);        // the MMAs that read this H~ buffer two chunks ago are done
-            WS_MARK(6);
-            if (eh < ksteps && q_unit < H) {
-                unsigned char* Hhi = smraw + L.hhi[b]; unsigned char* Hlo = smraw + L.hlo[b];
-                const int rbase = (q_unit >> 3) * SBO + (q_unit & 7) * 16 + 2 * eh * LBO;
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    float h[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int e = 8 * eh + 4 * g + j;
-                        float pre = __uint_as_float(v[4 * g + j]) + hb;
-                        if (sg.P_nbr) pre += Ps[e * H + q_unit];
-                        h[j] = e < n ? fmaxf(pre, 0.0f) : 0.0f;
-                    }
-                    float4 hi, lo;
-                    split_tf32(h[0], hi.x, lo.x); split_tf32(h[1], hi.y, lo.y); split_tf32(h[2], hi.z, lo.z); split_tf32(h[3], hi.w, lo.w);
-                    *reinterpret_cast<float4*>(Hhi + rbase + g * LBO) = hi;
-                    *reinterpret_cast<float4*>(Hlo + rbase + g * LBO) = lo;
+            if (lane == 0) mbar_arrive(&e_full[k & 1]);
+            return hb;
+        };
+        auto end_of_work = [&](int k) {          // tell the issuer that chunk k does not exist
+            if (ht == 0) ictl_e[k & 1] = 0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&e_full[k & 1]);
+        };
+        mbar_wait_ws(&raw_full[0], 0);
+        ChunkDesc d = cdesc[0];
+        float hb = 0.0f;
+        if (!d.valid) {
+            end_of_work(0);
+        } else {
+            hb = e_phase(0, d, 0, 0.0f);
+#pragma unroll 1
+            for (int c = 0;; ++c) {
+                const int s = c % NS, b = c & 1, s1 = (c + 1) % NS;
+                // ---- look ahead: the E tile of chunk c+1 goes out before this chunk's pre-activations are awaited, so the tensor
+                // pipe runs hidden(c+1) BEFORE main(c) and the H~ tile of chunk c+1 is produced while main(c) executes.  Not when
+                // chunk c+1 opens a new slot: re-staging the W1 tiles must wait for hidden(c) (done below, after the wait).
+                mbar_wait_ws(&raw_full[s1], ((c + 1) / NS) & 1);
+                WS_MARK(0);
+                const ChunkDesc d1 = cdesc[s1];
+                const bool early = d1.valid && !((d1.flags & 1) && staged_slot != d1.q);
+                float hb1 = hb;
+                if (early) hb1 = e_phase(c + 1, d1, s1, hb);
+                WS_MARK(1);
+                // ---- H-phase of chunk c
+                const cb_tp_segment& sg = a.segs[d.seg];
+                const float* Ps = reinterpret_cast<const float*>(stage_ptr(s) + L.o_ps);
+                const int n = d.n, ksteps = (n + 7) >> 3;
+                mbar_wait_ws(&hid_done[b], (c >> 1) & 1);
+                WS_MARK(4);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t v[8];
+                if (eh < ksteps) {       // warp-uniform
+                    const uint32_t taddr = tmem_hid + (uint32_t)(16 * b) + ((uint32_t)(lg * 32) << 16) + (uint32_t)(8 * eh);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                                 : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 }
+                WS_MARK(5);
+                mbar_wait_ws(&h_free[b], ((c >> 1) & 1) ^ 1);        // the MMAs that read this H~ buffer two chunks ago are done
+                WS_MARK(6);
+                if (eh < ksteps && q_unit < H) {
+                    unsigned char* Hhi = smraw + L.hhi[b]; unsigned char* Hlo = smraw + L.hlo[b];
+                    const int rbase = (q_unit >> 3) * SBO + (q_unit & 7) * 16 + 2 * eh * LBO;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        float h[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = 8 * eh + 4 * g + j;
+                            float pre = __uint_as_float(v[4 * g + j]) + hb;
+                            if (sg.P_nbr) pre += Ps[e * H + q_unit];
+                            h[j] = e < n ? fmaxf(pre, 0.0f) : 0.0f;
+                        }
+                        float4 hi, lo;
+                        split_tf32(h[0], hi.x, lo.x); split_tf32(h[1], hi.y, lo.y); split_tf32(h[2], hi.z, lo.z); split_tf32(h[3], hi.w, lo.w);
+                        *reinterpret_cast<float4*>(Hhi + rbase + g * LBO) = hi;
+                        *reinterpret_cast<float4*>(Hlo + rbase + g * LBO) = lo;
+                    }
+                }
+                if (ht == 0) ictl_m[b] = make_int4(d.flags, d.item_seq, d.n, 0);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&h_full[b]); mbar_arrive(&raw_empty[s]); }
+                WS_MARK(7);
+                if (!early) {
+                    if (!d1.valid) { end_of_work(c + 1); break; }
+                    hb1 = e_phase(c + 1, d1, s1, hb);      // new slot: hidden(c) has completed, the W1 tiles may be re-staged
+                }
+                hb = hb1;
+                d = d1;
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(&h_full[b]); mbar_arrive(&raw_empty[s]); }
-            WS_MARK(7);
         }
         if (ht == 0) WS_FLUSH(0);
         if (ht == 255) WS_FLUSH(1);
@@ -475,75 +519,80 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         // =============================================================== I: the CTA's MMA issuer (one thread)
         if (lane == 0) {
             const uint64_t d_w1hi = make_desc_sbo(smem_u32(smraw + L.w1hi), SBOW), d_w1lo = make_desc_sbo(smem_u32(smraw + L.w1lo), SBOW);
-            const uint64_t d_ehi = make_desc_sbo(smem_u32(smraw + L.ehi), SBOW), d_elo = make_desc_sbo(smem_u32(smraw + L.elo), SBOW);
+            const uint64_t d_e0h = make_desc_sbo(smem_u32(smraw + L.ehi[0]), SBOW), d_e0l = make_desc_sbo(smem_u32(smraw + L.elo[0]), SBOW);
+            const uint64_t d_e1h = make_desc_sbo(smem_u32(smraw + L.ehi[1]), SBOW), d_e1l = make_desc_sbo(smem_u32(smraw + L.elo[1]), SBOW);
             const uint64_t d_f0h = make_desc(smem_u32(smraw + L.fhi[0])), d_f0l = make_desc(smem_u32(smraw + L.flo[0]));
             const uint64_t d_f1h = make_desc(smem_u32(smraw + L.fhi[1])), d_f1l = make_desc(smem_u32(smraw + L.flo[1]));
             const uint64_t d_h0h = make_desc(smem_u32(smraw + L.hhi[0])), d_h0l = make_desc(smem_u32(smraw + L.hlo[0]));
             const uint64_t d_h1h = make_desc(smem_u32(smraw + L.hhi[1])), d_h1l = make_desc(smem_u32(smraw + L.hlo[1]));
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NRP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_h = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            auto issue_hidden = [&](int c) {      // pre[q][e] = sum_k W1e[q][k] e_attr[e][k] of chunk c (E tile published by the H warps)
-                mbar_wait_ws(&e_full, c & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint64_t dwh = d_w1hi, dwl = d_w1lo, deh = d_ehi, del = d_elo;
-#pragma unroll 2
-                for (int ks = 0; ks < ne / 8; ++ks) {
-                    mma_tf32(tmem_hid, dwh, deh, idesc_h, ks > 0 ? 1u : 0u);
-                    mma_tf32(tmem_hid, dwh, del, idesc_h, 1u);
-                    mma_tf32(tmem_hid, dwl, deh, idesc_h, 1u);
-                    dwh += (2 * LBO) >> 4; dwl += (2 * LBO) >> 4; deh += (2 * LBO) >> 4; del += (2 * LBO) >> 4;
-                }
-                umma_commit(&hid_done);
-            };
-            // chunk descriptors are read one chunk ahead (the stage is released to the scheduler right after the read)
-            mbar_wait_ws(&raw_full[0], 0);
-            ChunkDesc d = cdesc[0];
-            mbar_arrive(&raw_empty[0]);
-            if (d.valid) issue_hidden(0);
+            // Two in-order queues -- hidden(k) waits for the E tile of chunk k, main(k) for the H~ and F^T tiles of chunk k -- are
+            // polled and served in whichever order they become ready.  The interleaving only decides overlap: each queue writes
+            // its own TMEM columns in a fixed order, so the sums stay bit-reproducible.
+            int kh = 0, km = 0, end = 0x7fffffff, last_seq = -1;
+            long long t0 = clock64();
 #pragma unroll 1
-            for (int c = 0;; ++c) {
-                if (!d.valid) {
-                    // end of work: hand the sentinel to the epilogue warps through the next accumulator's barrier, with the flow
-                    // control of a real item (the epilogue must have consumed the previous phase of that barrier)
-                    const int seq = d.item_seq + 1;
-                    mbar_wait_ws(&acc_empty[seq & 1], ((seq >> 1) & 1) ^ 1);
-                    ItemDesc it; it.ws_off = 0; it.row_stride = 0; it.valid = 0;
-                    idesc_ring[seq % NI] = it;
+            while (km < end) {
+                bool progressed = false;
+                if (kh < end && mbar_test(&e_full[kh & 1], (kh >> 1) & 1)) {
                     asm volatile("fence.acq_rel.cta;" ::: "memory");
-                    mbar_arrive(&acc_full[seq & 1]);
-                    break;
+                    if (ictl_e[kh & 1] == 0) {
+                        end = kh;
+                    } else {
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const int eb = kh & 1;
+                        uint64_t dwh = d_w1hi, dwl = d_w1lo, deh = eb ? d_e1h : d_e0h, del = eb ? d_e1l : d_e0l;
+                        const uint32_t dh = tmem_hid + (uint32_t)(16 * eb);
+#pragma unroll 2
+                        for (int ks = 0; ks < ne / 8; ++ks) {
+                            mma_tf32(dh, dwh, deh, idesc_h, ks > 0 ? 1u : 0u);
+                            mma_tf32(dh, dwh, del, idesc_h, 1u);
+                            mma_tf32(dh, dwl, deh, idesc_h, 1u);
+                            dwh += (2 * LBO) >> 4; dwl += (2 * LBO) >> 4; deh += (2 * LBO) >> 4; del += (2 * LBO) >> 4;
+                        }
+                        umma_commit(&hid_done[eb]);
+                        ++kh;
+                    }
+                    progressed = true;
                 }
-                const int b = c & 1;
-                const int s1 = (c + 1) % NS;
-                mbar_wait_ws(&raw_full[s1], ((c + 1) / NS) & 1);
-                const ChunkDesc d1 = cdesc[s1];
-                mbar_arrive(&raw_empty[s1]);
-                // main(c): needs H~(c) and F^T(c); a new item also needs its accumulator drained by the epilogue
-                mbar_wait_ws(&h_full[b], (c >> 1) & 1);
-                mbar_wait_ws(&f_full[b], (c >> 1) & 1);
-                const int acc = d.item_seq & 1;
-                if (d.flags & 1) mbar_wait_ws(&acc_empty[acc], ((d.item_seq >> 1) & 1) ^ 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t dacc = tmem_base + (uint32_t)(acc * ACC_COLS);
-                const uint32_t acc0 = (d.flags & 1) ? 0u : 1u;
-                const uint64_t fh = b ? d_f1h : d_f0h, fl = b ? d_f1l : d_f0l, hh = b ? d_h1h : d_h0h, hl = b ? d_h1l : d_h0l;
-                mma_tf32(dacc, hh, fh, idesc, acc0);
-                mma_tf32(dacc, hh, fl, idesc, 1u);
-                mma_tf32(dacc, hl, fh, idesc, 1u);
-                if (((d.n + 7) >> 3) > 1) {
-                    const uint64_t ks = (uint64_t)((2 * LBO) >> 4);
-                    mma_tf32(dacc, hh + ks, fh + ks, idesc, 1u);
-                    mma_tf32(dacc, hh + ks, fl + ks, idesc, 1u);
-                    mma_tf32(dacc, hl + ks, fh + ks, idesc, 1u);
+                if (km < kh && km < end && mbar_test(&h_full[km & 1], (km >> 1) & 1) && mbar_test(&f_full[km & 1], (km >> 1) & 1)) {
+                    asm volatile("fence.acq_rel.cta;" ::: "memory");
+                    const int b = km & 1;
+                    const int4 ctl = ictl_m[b];          // (flags, item_seq, n)
+                    const int acc = ctl.y & 1;
+                    if (ctl.x & 1) mbar_wait_ws(&acc_empty[acc], ((ctl.y >> 1) & 1) ^ 1);   // the epilogue of item_seq - 2 has drained it
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t dacc = tmem_base + (uint32_t)(acc * ACC_COLS);
+                    const uint32_t acc0 = (ctl.x & 1) ? 0u : 1u;
+                    const uint64_t fh = b ? d_f1h : d_f0h, fl = b ? d_f1l : d_f0l, hh = b ? d_h1h : d_h0h, hl = b ? d_h1l : d_h0l;
+                    mma_tf32(dacc, hh, fh, idesc, acc0);
+                    mma_tf32(dacc, hh, fl, idesc, 1u);
+                    mma_tf32(dacc, hl, fh, idesc, 1u);
+                    if (((ctl.z + 7) >> 3) > 1) {
+                        const uint64_t ks = (uint64_t)((2 * LBO) >> 4);
+                        mma_tf32(dacc, hh + ks, fh + ks, idesc, 1u);
+                        mma_tf32(dacc, hh + ks, fl + ks, idesc, 1u);
+                        mma_tf32(dacc, hl + ks, fh + ks, idesc, 1u);
+                    }
+                    umma_commit(&f_free[b]);
+                    umma_commit(&h_free[b]);
+                    if (ctl.x & 2) umma_commit(&acc_full[acc]);
+                    last_seq = ctl.y;
+                    ++km;
+                    progressed = true;
                 }
-                umma_commit(&f_free[b]);
-                umma_commit(&h_free[b]);
-                if (d.flags & 2) umma_commit(&acc_full[acc]);
-                // hidden(c+1) right behind main(c): its E tile is published by the H warps after they finished H~(c), and they
-                // read the pre-activations back while the tensor pipe is still busy with main(c)
-                if (d1.valid) issue_hidden(c + 1);
-                d = d1;
+                if (progressed) t0 = clock64();
+                else if (clock64() - t0 > 6000000000ll) __trap();      // bounded: ~3 s without progress
             }
+            // end of work: hand the sentinel to the epilogue warps through the next accumulator's barrier, with the flow control of
+            // a real item (the epilogue must have consumed the previous phase of that barrier)
+            const int seq = last_seq + 1;
+            mbar_wait_ws(&acc_empty[seq & 1], ((seq >> 1) & 1) ^ 1);
+            ItemDesc it; it.ws_off = 0; it.row_stride = 0; it.valid = 0;
+            idesc_ring[seq % NI] = it;
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            mbar_arrive(&acc_full[seq & 1]);
         }
     } else {
         // =============================================================== E: epilogue (TMEM -> registers -> workspace)
