@@ -40,7 +40,7 @@ class TpSegment(C.Structure):
         ("W1e", C.c_void_p), ("ldw1", C.c_int32),
         ("b1", C.c_void_p), ("W2a", C.c_void_p),
         ("n0", C.c_int32), ("n1", C.c_int32), ("col_off", C.c_int32), ("slot", C.c_int32),
-        ("gate_rowptr", C.c_void_p), ("gate_mask", C.c_void_p),
+        ("gate_rowptr", C.c_void_p), ("gate_mask", C.c_void_p), ("W2t", C.c_void_p),
     ]
 
 
@@ -60,6 +60,8 @@ class TpConvArgs(C.Structure):
         ("accum_mode", C.c_int32), ("flags", C.c_int32),
         ("pre_sum", C.c_void_p), ("pre_deg", C.c_void_p), ("pre_n0", C.c_int32), ("pre_n1", C.c_int32),
         ("pre_period", C.c_int32), ("pad_", C.c_int32),
+        ("chains", C.c_void_p), ("n_chains", C.c_int32), ("blocks", C.c_void_p), ("n_blocks", C.c_int32),
+        ("kp", C.c_int32), ("max_chain_bytes", C.c_int32),
     ]
 
 

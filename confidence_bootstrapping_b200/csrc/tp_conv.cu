@@ -1495,6 +1495,8 @@ tp_transform_kernel(const __grid_constant__ cb_tp_conv_args a) {
     }
 }
 
+#include "tp_transform_tc.cuh"
+
 }  // namespace tf
 
 template <class C>
@@ -1639,6 +1641,23 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
         return CB_ERR_CUDA;
     }
     const int tiles = cb_div_up(a->node_end - a->node_begin, tf::NB);
+    // tensor-core transform: big launches of layers with a plan (cb200.h); small ones keep the FFMA kernel and its run split
+    bool use_tc = a->chains != nullptr && a->blocks != nullptr && a->n_chains > 0 && tiles * 2 > CB_NUM_SMS && (H + PADC) % 4 == 0;
+    for (int s = 0; s < a->n_segs && use_tc; ++s) use_tc = a->segs[s].W2t != nullptr;
+    if (use_tc) {
+        const tf::tt::LayoutTT LT = tf::tt::make_layout_tt(H + PADC, a->kp, a->d_out, a->n_chains, a->n_blocks, t.n_slots, a->max_chain_bytes);
+        use_tc = LT.total <= 225 * 1024;
+        if (use_tc) {
+            cudaError_t e2 = cudaFuncSetAttribute(tf::tt::tp_transform_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT.total);
+            if (e2 != cudaSuccess) {
+                cb_set_error("cb_tp_conv_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
+                return CB_ERR_CUDA;
+            }
+            tf::tt::tp_transform_tc_kernel<<<tiles, tf::tt::THREADS_TT, LT.total, st>>>(*a, a->max_chain_bytes);
+            CB_CHECK_LAUNCH("cb_tp_conv_forward(transform, tcgen05)");
+            return CB_OK;
+        }
+    }
     // launches with few node tiles are chains of row groups on a handful of SMs: split each tile's runs over up to 8 CTAs
     int n_split = 1;
     while (n_split < 8 && n_split < a->n_runs && tiles * n_split * 2 <= CB_NUM_SMS * 3) n_split *= 2;

@@ -313,3 +313,68 @@ def full_tp_low_blocks(lmax: int):
     blocks.sort(key=lambda b: (b[0], b[1]))
     irreps = " + ".join(f"1x{lo}{'e' if p == 1 else 'o'}" for lo, p, _ in blocks)
     return irreps, [(l1, wigner_3j(l1, 2, lo) * math.sqrt(2 * lo + 1)) for lo, p, l1 in blocks]
+
+
+# ----------------------------------------------------------------------------- tensor-core transform plan
+CHAIN_DTYPE = np.dtype([("row0", "<i4"), ("row1", "<i4"), ("row2", "<i4"), ("n_comp", "<i4"), ("w_off", "<i4"), ("npad", "<i4"),
+                        ("acc_col", "<i4"), ("first", "<i4")])
+BLOCK_DTYPE = np.dtype([("n_comp", "<i4"), ("mul", "<i4"), ("npad", "<i4"), ("acc_col0", "<i4"), ("n_partials", "<i4"),
+                        ("out_step", "<i4"), ("out_base0", "<i4"), ("out_base1", "<i4"), ("out_base2", "<i4"), ("pad0", "<i4"),
+                        ("pad1", "<i4"), ("pad2", "<i4")])
+MAX_CHAIN_MMAS = 600     # MMAs accumulated into one TMEM partial sum (fp32 accumulation error grows with the chain length)
+
+
+@dataclass
+class TransformPlan:
+    """How the tcgen05 transform kernel (tp_transform_tc.cuh) walks a layer's program.
+
+    A *block* = the runs (one per output component) that share their weight rows: for every u of the block the kernel
+    stacks the components' accumulator rows (row_c + u) along M (component c, node rank) and multiplies by the `mul` weight rows
+    of u -- one MMA chain D[(c, rank)][m] += A[(c, rank)][:] . W[u, m][:].  Chains of a block go to `n_partials` TMEM partial
+    sums of at most MAX_CHAIN_MMAS MMAs each, which the epilogue adds in fp32."""
+    chains: np.ndarray      # CHAIN_DTYPE
+    blocks: np.ndarray      # BLOCK_DTYPE
+    kp: int                 # K padded to the MMA's k-step (8)
+    w_floats: int           # floats of one group's W tile buffer
+    acc_cols: int           # TMEM columns of one accumulator set
+    w_index: list           # per chain: (first weight row, mul, npad) for building the W tiles
+
+
+def transform_plan(prog: TPProgram, H: int):
+    """None when the program does not fit the tensor-core transform (more than 3 stacked components, > 32 outputs per row,
+    more than 256 TMEM columns per accumulator set)."""
+    ha = H + 4
+    kp = (ha + 7) // 8 * 8
+    mmas_per_chain = (kp // 8) * 3
+    upp = max(1, MAX_CHAIN_MMAS // mmas_per_chain)
+    runs = prog.runs
+    groups = {}
+    for r in runs:          # runs that share their weights = the components of one block
+        key = (int(r["w_base0"]), int(r["mul"]), int(r["row_end"] - r["row_begin"]), int(r["out_step"]))
+        groups.setdefault(key, []).append(r)
+    chains, blocks, w_index = [], [], []
+    acc_col = 0
+    w_off = 0
+    for (w_base0, mul, n_u, out_step), rs in groups.items():
+        if len(rs) > 3 or mul > 32:
+            return None
+        npad = (mul + 15) // 16 * 16
+        n_part = -(-n_u // upp)
+        ob = [int(r["out_base"]) for r in rs] + [0, 0, 0]
+        blocks.append((len(rs), mul, npad, acc_col, n_part, out_step, ob[0], ob[1], ob[2], 0, 0, 0))
+        rows0 = [int(r["row_begin"]) for r in rs] + [-1, -1, -1]
+        for u in range(n_u):
+            chains.append((rows0[0] + u, rows0[1] + u if rows0[1] >= 0 else -1, rows0[2] + u if rows0[2] >= 0 else -1, len(rs), w_off, npad,
+                           acc_col + (u // upp) * npad, int(u % upp == 0)))
+            w_index.append((w_base0 + u * mul, mul, npad))
+            w_off += 2 * npad * kp
+        acc_col += n_part * npad
+    if acc_col > 256:
+        return None
+    ch = np.zeros(len(chains), dtype=CHAIN_DTYPE)
+    for k, c in enumerate(chains):
+        ch[k] = c
+    bl = np.zeros(len(blocks), dtype=BLOCK_DTYPE)
+    for k, b in enumerate(blocks):
+        bl[k] = b
+    return TransformPlan(ch, bl, kp, w_off, acc_col, w_index)

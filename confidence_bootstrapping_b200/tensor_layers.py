@@ -19,7 +19,7 @@ from torch import nn
 from . import _lib
 from .graph import EdgeList, static_edges
 from .irreps import (TPProgram, faster_tp_program, fctp_program, get_irrep_seq, irreps_dim, irreps_str,
-                     parse_irreps, sh_irreps)
+                     parse_irreps, sh_irreps, transform_plan)
 
 ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
 # accumulate kernel of K3: 3 = tcgen05 3xTF32 UMMA with the TRANSPOSED TMEM accumulator (default; layers with more than 240
@@ -27,6 +27,7 @@ ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
 # 1 = fp32 FFMA register tiles (kept for shapes outside the UMMA tile limits and for A/B measurements)
 ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "3"))
 FOLD_E_POST = True            # fold W1e.e_post[graph] into the node projection on the host (tests switch it off to cover the kernel path)
+TC_TRANSFORM = os.environ.get("CB200_TC_TRANSFORM", "1") != "0"   # tcgen05 transform kernel for big launches (FFMA kernel otherwise)
 DEBUG_KEEP_WORKSPACE = None   # tests may set this to a list to inspect the K3 accumulators
 WORKSPACE_BYTES = int(os.environ.get("CB200_WORKSPACE_MB", str(16 << 10))) << 20  # cap on the K3 accumulator workspace (180 GB of HBM3e per GPU); larger layers run in node chunks
 
@@ -114,6 +115,11 @@ class Segment:
     slot: Optional[int] = None           # segments sharing a slot share (n0, n1, group) and one accumulator
 
 
+def _tf32_round(x):
+    """fp32 -> nearest value with a 10-bit mantissa (what tcgen05 kind::tf32 keeps), as fp32."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+
+
 class _DeviceProgram:
     def __init__(self, prog: TPProgram, device):
         self.prog = prog
@@ -154,6 +160,8 @@ class TensorProductConvLayer(nn.Module):
                                              dropout, activation) for _ in range(edge_groups)])
         self.batch_norm = EquivariantBatchNorm(out_irreps) if batch_norm else None
         self._dev_prog = None
+        self._plan = None          # tensor-core transform plan (irreps.transform_plan) + its device tables
+        self._w2t_cache = {}
         self._w2a_cache = {}
         self._param_cache = {}
         self._proj_cache = {}
@@ -164,17 +172,18 @@ class TensorProductConvLayer(nn.Module):
         (data_ptr, _version), which misses in-place writes through `param.data` (EMA copy_to / restore, utils/utils.py:353-392):
         `sampling()` calls this on the model at the start of every call, and `.to()` / `load_state_dict` / `train()` do too."""
         self._w2a_cache.clear()
+        self._w2t_cache.clear()
         self._proj_cache.clear()
         self._param_cache.clear()
         if self.batch_norm is not None:
             self.batch_norm.invalidate_caches()
 
     def _apply(self, fn, *a, **kw):
-        self._w2a_cache.clear(); self._proj_cache.clear(); self._param_cache.clear()
+        self._w2a_cache.clear(); self._w2t_cache.clear(); self._proj_cache.clear(); self._param_cache.clear()
         return super()._apply(fn, *a, **kw)
 
     def _load_from_state_dict(self, *a, **kw):
-        self._w2a_cache.clear(); self._proj_cache.clear(); self._param_cache.clear()
+        self._w2a_cache.clear(); self._w2t_cache.clear(); self._proj_cache.clear(); self._param_cache.clear()
         return super()._load_from_state_dict(*a, **kw)
 
     def train(self, mode=True):
@@ -207,6 +216,50 @@ class TensorProductConvLayer(nn.Module):
                 t[:, W2.shape[1]] = b2
             hit = (key, t)
             self._w2a_cache[g] = hit
+        return hit[1]
+
+    def _tc_plan(self, device):
+        """(TransformPlan, chains tensor, blocks tensor, max staging bytes) or None when the program does not fit the kernel."""
+        if self._plan is None or (self._plan is not False and self._plan[1].device != device):
+            plan = transform_plan(self.program, self.hidden_features)
+            if plan is None:
+                self._plan = False
+            else:
+                ha = self.hidden_features + 4
+                stage = max(int(c["n_comp"]) * 32 * ha * 4 + 2 * int(c["npad"]) * plan.kp * 4 for c in plan.chains)
+                self._plan = (plan, torch.from_numpy(plan.chains.view(np.uint8).copy()).to(device),
+                              torch.from_numpy(plan.blocks.view(np.uint8).copy()).to(device), stage)
+        return self._plan or None
+
+    def _w2t(self, g, plan):
+        """W2a of group g re-laid for the tensor-core transform: per chain [hi | lo] tiles of `npad` weight rows x kp columns in
+        the K-major core-matrix layout (element (n, k) of a tile at (n // 8) * (kp // 4 * 32) + (k // 4) * 32 + (n % 8) * 4 + k % 4),
+        hi = TF32-rounded weight, lo = TF32-rounded remainder.  Rebuilt when the parameters change (same key as _w2a)."""
+        W2a = self._w2a(g)
+        key = self._w2a_cache[g][0]
+        hit = self._w2t_cache.get(g)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                kp, ha = plan.kp, W2a.shape[1]
+                out = torch.zeros(plan.w_floats, dtype=torch.float32, device=W2a.device)
+                for npad in sorted({w[2] for w in plan.w_index}):
+                    idx = [k for k, w in enumerate(plan.w_index) if w[2] == npad]
+                    mul = plan.w_index[idx[0]][1]
+                    assert all(plan.w_index[k][1] == mul for k in idx)
+                    rows0 = torch.tensor([plan.w_index[k][0] for k in idx], device=W2a.device)
+                    offs = torch.tensor([int(plan.chains["w_off"][k]) for k in idx], device=W2a.device)
+                    w = torch.zeros((len(idx), npad, kp), dtype=torch.float32, device=W2a.device)
+                    w[:, :mul, :ha] = W2a[(rows0[:, None] + torch.arange(mul, device=W2a.device)[None, :])]
+                    hi = _tf32_round(w)
+                    lo = _tf32_round(w - hi)
+                    # (n, k) -> [n // 8][k // 4][n % 8][k % 4]
+                    def tile(t):
+                        return t.view(len(idx), npad // 8, 8, kp // 4, 4).permute(0, 1, 3, 2, 4).reshape(len(idx), npad * kp)
+                    both = torch.cat([tile(hi), tile(lo)], dim=1)          # [chains, 2 * npad * kp]
+                    pos = offs[:, None] + torch.arange(2 * npad * kp, device=W2a.device)[None, :]
+                    out[pos.reshape(-1)] = both.reshape(-1)
+            hit = (key, out)
+            self._w2t_cache[g] = hit
         return hit[1]
 
     def _projection(self, groups, cols):
@@ -301,10 +354,18 @@ class TensorProductConvLayer(nn.Module):
             key = (s.group, s.n0, s.n1, None if s.e_post is None else s.e_post.data_ptr()) if s.slot is None else ("id", s.slot)
             slot_ids.append(slot_ids[-1] + (key != prev) if slot_ids else 0)
             prev = key
+        tcp = self._tc_plan(dev) if TC_TRANSFORM else None
+        if tcp is not None:
+            plan, chains_t, blocks_t, stage_bytes = tcp
+            a.chains, a.n_chains = chains_t.data_ptr(), len(plan.chains)
+            a.blocks, a.n_blocks = blocks_t.data_ptr(), len(plan.blocks)
+            a.kp, a.max_chain_bytes = plan.kp, stage_bytes
         for k, s in enumerate(segments):
             W1, b1 = self._params(s.group)[:2]
             W2a = self._w2a(s.group)
             sg = a.segs[k]
+            if tcp is not None:
+                sg.W2t = self._w2t(s.group, tcp[0]).data_ptr()
             sg.rowptr, sg.col = _lib.i32(s.edges.rowptr, "rowptr"), _lib.i32(s.edges.col, "col")
             sg.e_attr, sg.sh = _lib.f32(s.e_attr, "e_attr"), _lib.f32(s.sh, "sh")
             assert s.e_attr.shape[1] == e_cols[1] and s.sh.shape[1] == P.sh_dim

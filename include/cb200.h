@@ -153,7 +153,17 @@ typedef struct {
                                with no edge there are skipped (treated as degree 0) -- dead-output pruning, e.g. receptor
                                rows of the last full conv layer that no rec->lig edge reads (score_model.py:372-374) */
     const uint8_t* gate_mask;   /* optional [n1-n0] keep flags with the same effect (0 = skip the node in this segment)   */
+    const float* W2t;       /* optional: W2a re-laid for the tensor-core transform (cb_tp_chain.w_off indexes it): per chain
+                               the hi then the lo TF32 part of the chain's `npad` weight rows as K-major core-matrix tiles  */
 } cb_tp_segment;
+typedef struct {            /* one MMA chain of the tensor-core transform: accumulator rows row[c] (one per stacked
+                               output component, -1 = unused) times the weight tile at W2t + w_off                         */
+    int32_t row[3]; int32_t n_comp, w_off, npad, acc_col, first;
+} cb_tp_chain;
+typedef struct {            /* one output block (components sharing their weights): where its partial sums sit in TMEM and
+                               which output channels they feed: out_base[c] + m * out_step                                  */
+    int32_t n_comp, mul, npad, acc_col0, n_partials, out_step; int32_t out_base[3]; int32_t pad_[3];
+} cb_tp_block;
 #define CB_MAX_SEGS 12
 typedef struct {
     const float* x;         /* [N_in, d_in] node features gathered at col                        */
@@ -187,6 +197,11 @@ typedef struct {
     const float* pre_sum;   /* [pre_period, d_out]                                               */
     const int32_t* pre_deg; /* [pre_period]                                                      */
     int32_t pre_n0, pre_n1, pre_period, pad_;
+    /* tensor-core transform plan (optional; built once per layer on the host, irreps.transform_plan): when present and every
+     * segment carries W2t, launches with enough node tiles run the tcgen05 transform kernel instead of the FFMA one          */
+    const cb_tp_chain* chains; int32_t n_chains;
+    const cb_tp_block* blocks; int32_t n_blocks;
+    int32_t kp, max_chain_bytes;   /* K padded to 8; largest (raw rows + W tile) staging footprint of a chain in bytes */
 } cb_tp_conv_args;
 #define CB_TP_RAW_SUM 1
 /* number of (node, slot) accumulators the call will use (host arithmetic only) */
