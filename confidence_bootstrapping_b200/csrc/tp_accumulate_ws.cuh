@@ -99,10 +99,14 @@ __host__ __device__ inline LayoutWS make_layout_ws(int n_rows, int n_terms, int 
     return L;
 }
 
+constexpr uint32_t WS_SUSPEND_NS = 100000u;      // per try_wait; a lost arrival traps after WS_SUSPEND_TRIES failed waits
+constexpr uint32_t WS_SUSPEND_TRIES = 4000000u;   // >= 1.5 s even if the hardware caps the suspension at a few hundred ns
+
 // bounded wait: a lost arrival traps after ~1.5 s of spinning instead of hanging the GPU (the kernel itself runs ~1 ms)
 // (An out-of-line copy and a sleep between polls were both measured slower.)
 __device__ __forceinline__ void mbar_wait_ws(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#ifndef CB_WS_SUSPEND_WAIT
     const long long t0 = clock64();
 #pragma unroll 1
     for (unsigned spin = 0;; ++spin) {
@@ -114,6 +118,29 @@ __device__ __forceinline__ void mbar_wait_ws(uint64_t* bar, uint32_t parity) {
         if (ok) return;
         if ((spin & 255u) == 255u && clock64() - t0 > 3000000000ll) __trap();
     }
+#else
+    // experiment (-DCB_WS_SUSPEND_WAIT): try_wait with a suspend-time hint, so that the hardware parks the warp instead of
+    // re-issuing the poll (the spin loops are 70 % of the executed instructions of this kernel).  Measured: no change
+    // (conv layer 1: 1.047 ms vs 1.055 ms) -- the polls do not take issue slots anybody else wants.
+#pragma unroll 1
+    for (unsigned spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity), "r"(WS_SUSPEND_NS)
+                     : "memory");
+        if (ok) return;
+        if (spin > WS_SUSPEND_TRIES) __trap();
+    }
+#endif
+}
+
+// UMMA shared-memory descriptor of a K-major tile in a SWIZZLED layout (rows of 64 or 128 bytes, 8-row atoms, 16-byte chunks
+// XOR-ed with the row index): start >> 4 | LBO (unused for K-major swizzled: 1) << 16 | SBO >> 4 << 32 | version 1 << 46 | layout << 61
+// (layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B).  The tensor core reads a no-swizzle tile one 128-byte core matrix at a time --
+// measured ~100 cycles per M = 128 MMA whatever N -- while a swizzled row is fetched at full shared-memory width.
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, int sbo_bytes, int layout) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 
 // non-blocking: has the phase with this parity completed?
@@ -202,6 +229,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         int item = blockIdx.x, q = 0, item_seq = -1;
         int c = 0;                   // chunk counter of this CTA
         bool done = false;
+        WS_T0();
 #pragma unroll 1
         while (!done) {
             // ---- next item with at least one edge
@@ -235,7 +263,9 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
 #pragma unroll 1
             while (true) {
                 const int s = c % NS;
+                WS_MARK(1);
                 mbar_wait_ws(&raw_empty[s], ((c / NS) & 1) ^ 1);
+                WS_MARK(0);
                 ChunkDesc d;
                 d.valid = done ? 0 : 1; d.seg = seg; d.item_seq = item_seq; d.node = node; d.q = q; d.pad = e0;   // pad = first edge
                 bool last = true;
@@ -268,15 +298,19 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             }
             if (!done) item += (int)gridDim.x;
         }
+        if (lane == 0) WS_FLUSH(3);
     } else if (warp >= W_G0 && warp < W_I) {
         // =============================================================== G: gather warps (edges g, g+4, g+8, g+12 of every chunk)
         const int g = warp - W_G0;
         int pending = 0;
         int c = 0;
+        WS_T0();
 #pragma unroll 1
         for (;; ++c) {
             const int s = c % NS;
+            WS_MARK(2);
             mbar_wait_ws(&desc_full[s], (c / NS) & 1);
+            WS_MARK(0);
             const ChunkDesc d = cdesc[s];
             if (d.valid) {
                 const cb_tp_segment& sg = a.segs[d.seg];
@@ -315,6 +349,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 for (int i = g * 32 + lane; i < n * (ne / 4); i += 32 * G_WARPS) cp_async_bytes16(es + 4 * i, sg.e_attr + (size_t)base * ne + 4 * i);
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
+            WS_MARK(1);
             ++pending;
             // publish the chunk issued LAG iterations ago: this warp's copies for it have landed
             if (pending > LAG) {
@@ -331,6 +366,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
 #pragma unroll 1
         for (; pending > 0; --pending)
             if (lane == 0) mbar_arrive(&raw_full[(c + 1 - pending) % NS]);
+        if (g == 0 && lane == 0) WS_FLUSH(4);
     } else if (warp < F_WARPS) {
         // =============================================================== F: f-rows -> F^T operand tiles
         int tb0 = 0, te0 = 0, t_xi[MAXT], t_si[MAXT];
@@ -344,19 +380,24 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
         }
         const int nt_warp = __reduce_max_sync(0xffffffffu, min(te0 - tb0, MAXT));
         float fsum = 0.0f;
+        WS_T0();
 #pragma unroll 1
         for (int c = 0;; ++c) {
             const int s = c % NS, fb = c & 1;
+            WS_MARK(3);
             mbar_wait_ws(&raw_full[s], (c / NS) & 1);
+            WS_MARK(0);
             const ChunkDesc d = cdesc[s];
             if (!d.valid) break;
-            mbar_wait_ws(&f_free[fb], ((c >> 1) & 1) ^ 1);         // the MMAs that read this tile buffer two chunks ago are done
+            mbar_wait_ws(&f_free[fb], ((c >> 1) & 1) ^ 1);
+            WS_MARK(1);         // the MMAs that read this tile buffer two chunks ago are done
             const unsigned char* stg = stage_ptr(s);
             const float* xs = reinterpret_cast<const float*>(stg + L.o_xs);
             const float* shs = reinterpret_cast<const float*>(stg + L.o_shs);
             const int n = d.n, nq = 2 * ((n + 7) >> 3);
             if (tid < n_rows) {
-                const FRowCtx fc{xs, shs, terms_s, smraw + L.fhi[fb], smraw + L.flo[fb], dxp, S, n, nq, tb0, te0, (tid >> 3) * SBO + (tid & 7) * 16};
+                const FRowCtx fc{xs, shs, terms_s, smraw + L.fhi[fb], smraw + L.flo[fb], dxp, S, n, nq, tb0, te0, (tid >> 3) * 512 + (tid & 7) * 64,
+                                 16, (tid & 7) >> 1};       // SWIZZLE_64B operand tile
                 float part;
                 switch (nt_warp) {
                     case 1: part = f_row<1>(fc, t_xi, t_si, t_cf); break;
@@ -369,11 +410,14 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy tile writes -> async proxy (UMMA)
             __syncwarp();
             if (lane == 0) { mbar_arrive(&f_full[fb]); mbar_arrive(&raw_empty[s]); }
+            WS_MARK(2);
             if ((d.flags & 2) && tid < n_rows) {       // column H of the workspace: sum_e f_e[r], then the zero pad the transform multiplies by 0
                 const ItemDesc it = idesc_ring[d.item_seq % NI];
                 *reinterpret_cast<float4*>(a.workspace + it.ws_off + (size_t)tid * it.row_stride + H) = make_float4(fsum, 0.f, 0.f, 0.f);
             }
         }
+        if (tid == 0) WS_FLUSH(2);
+        if (tid == 224) WS_FLUSH(7);
     } else if (warp < F_WARPS + H_WARPS) {
         // =============================================================== H: E tile (one chunk ahead), then pre-activations -> H~ tile
         const int hw = warp - F_WARPS;              // 0..7
@@ -400,7 +444,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                         const float4 w = __ldg(reinterpret_cast<const float4*>(s0.W1e + (size_t)qq * s0.ldw1) + c4);
                         float4 hi, lo;
                         split_tf32(w.x, hi.x, lo.x); split_tf32(w.y, hi.y, lo.y); split_tf32(w.z, hi.z, lo.z); split_tf32(w.w, hi.w, lo.w);
-                        const int off = (qq >> 3) * SBOW + c4 * LBO + (qq & 7) * 16;
+                        const int off = (qq >> 3) * 1024 + (qq & 7) * 128 + ((c4 ^ (qq & 7)) << 4);      // SWIZZLE_128B (ne = 32: 128-byte rows)
                         *reinterpret_cast<float4*>(W1hi + off) = hi;
                         *reinterpret_cast<float4*>(W1lo + off) = lo;
                     }
@@ -427,7 +471,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 const float4 v = *reinterpret_cast<const float4*>(es + e * ne + 4 * c4);     // rows >= n hold stale data: discarded later
                 float4 hi, lo;
                 split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-                const int off = (e >> 3) * SBOW + c4 * LBO + (e & 7) * 16;
+                const int off = (e >> 3) * 1024 + (e & 7) * 128 + ((c4 ^ (e & 7)) << 4);             // SWIZZLE_128B
                 *reinterpret_cast<float4*>(Ehi + off) = hi;
                 *reinterpret_cast<float4*>(Elo + off) = lo;
             }
@@ -482,7 +526,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 WS_MARK(6);
                 if (eh < ksteps && q_unit < H) {
                     unsigned char* Hhi = smraw + L.hhi[b]; unsigned char* Hlo = smraw + L.hlo[b];
-                    const int rbase = (q_unit >> 3) * SBO + (q_unit & 7) * 16 + 2 * eh * LBO;
+                    const int rbase = (q_unit >> 3) * 512 + (q_unit & 7) * 64;          // SWIZZLE_64B: 16-byte chunk j of the row at (j ^ row bits) * 16
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         float h[4];
@@ -495,8 +539,9 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                         }
                         float4 hi, lo;
                         split_tf32(h[0], hi.x, lo.x); split_tf32(h[1], hi.y, lo.y); split_tf32(h[2], hi.z, lo.z); split_tf32(h[3], hi.w, lo.w);
-                        *reinterpret_cast<float4*>(Hhi + rbase + g * LBO) = hi;
-                        *reinterpret_cast<float4*>(Hlo + rbase + g * LBO) = lo;
+                        const int coff = rbase + (((2 * eh + g) ^ ((q_unit & 7) >> 1)) << 4);
+                        *reinterpret_cast<float4*>(Hhi + coff) = hi;
+                        *reinterpret_cast<float4*>(Hlo + coff) = lo;
                     }
                 }
                 if (ht == 0) ictl_m[b] = make_int4(d.flags, d.item_seq, d.n, 0);
@@ -508,23 +553,24 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                 if (!early) {
                     if (!d1.valid) { end_of_work(c + 1); break; }
                     hb1 = e_phase(c + 1, d1, s1, hb);      // new slot: hidden(c) has completed, the W1 tiles may be re-staged
+                    WS_MARK(1);
                 }
                 hb = hb1;
                 d = d1;
             }
         }
         if (ht == 0) WS_FLUSH(0);
-        if (ht == 255) WS_FLUSH(1);
+        if (ht == 32) WS_FLUSH(1);
     } else if (warp == W_I) {
         // =============================================================== I: the CTA's MMA issuer (one thread)
         if (lane == 0) {
-            const uint64_t d_w1hi = make_desc_sbo(smem_u32(smraw + L.w1hi), SBOW), d_w1lo = make_desc_sbo(smem_u32(smraw + L.w1lo), SBOW);
-            const uint64_t d_e0h = make_desc_sbo(smem_u32(smraw + L.ehi[0]), SBOW), d_e0l = make_desc_sbo(smem_u32(smraw + L.elo[0]), SBOW);
-            const uint64_t d_e1h = make_desc_sbo(smem_u32(smraw + L.ehi[1]), SBOW), d_e1l = make_desc_sbo(smem_u32(smraw + L.elo[1]), SBOW);
-            const uint64_t d_f0h = make_desc(smem_u32(smraw + L.fhi[0])), d_f0l = make_desc(smem_u32(smraw + L.flo[0]));
-            const uint64_t d_f1h = make_desc(smem_u32(smraw + L.fhi[1])), d_f1l = make_desc(smem_u32(smraw + L.flo[1]));
-            const uint64_t d_h0h = make_desc(smem_u32(smraw + L.hhi[0])), d_h0l = make_desc(smem_u32(smraw + L.hlo[0]));
-            const uint64_t d_h1h = make_desc(smem_u32(smraw + L.hhi[1])), d_h1l = make_desc(smem_u32(smraw + L.hlo[1]));
+            const uint64_t d_w1hi = make_desc_sw(smem_u32(smraw + L.w1hi), 1024, 2), d_w1lo = make_desc_sw(smem_u32(smraw + L.w1lo), 1024, 2);
+            const uint64_t d_e0h = make_desc_sw(smem_u32(smraw + L.ehi[0]), 1024, 2), d_e0l = make_desc_sw(smem_u32(smraw + L.elo[0]), 1024, 2);
+            const uint64_t d_e1h = make_desc_sw(smem_u32(smraw + L.ehi[1]), 1024, 2), d_e1l = make_desc_sw(smem_u32(smraw + L.elo[1]), 1024, 2);
+            const uint64_t d_f0h = make_desc_sw(smem_u32(smraw + L.fhi[0]), 512, 4), d_f0l = make_desc_sw(smem_u32(smraw + L.flo[0]), 512, 4);
+            const uint64_t d_f1h = make_desc_sw(smem_u32(smraw + L.fhi[1]), 512, 4), d_f1l = make_desc_sw(smem_u32(smraw + L.flo[1]), 512, 4);
+            const uint64_t d_h0h = make_desc_sw(smem_u32(smraw + L.hhi[0]), 512, 4), d_h0l = make_desc_sw(smem_u32(smraw + L.hlo[0]), 512, 4);
+            const uint64_t d_h1h = make_desc_sw(smem_u32(smraw + L.hhi[1]), 512, 4), d_h1l = make_desc_sw(smem_u32(smraw + L.hlo[1]), 512, 4);
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NRP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_h = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             // Two in-order queues -- hidden(k) waits for the E tile of chunk k, main(k) for the H~ and F^T tiles of chunk k -- are
@@ -532,9 +578,11 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             // its own TMEM columns in a fixed order, so the sums stay bit-reproducible.
             int kh = 0, km = 0, end = 0x7fffffff, last_seq = -1;
             long long t0 = clock64();
+            WS_T0();
 #pragma unroll 1
             while (km < end) {
                 bool progressed = false;
+                WS_MARK(0);
                 if (kh < end && mbar_test(&e_full[kh & 1], (kh >> 1) & 1)) {
                     asm volatile("fence.acq_rel.cta;" ::: "memory");
                     if (ictl_e[kh & 1] == 0) {
@@ -549,19 +597,22 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                             mma_tf32(dh, dwh, deh, idesc_h, ks > 0 ? 1u : 0u);
                             mma_tf32(dh, dwh, del, idesc_h, 1u);
                             mma_tf32(dh, dwl, deh, idesc_h, 1u);
-                            dwh += (2 * LBO) >> 4; dwl += (2 * LBO) >> 4; deh += (2 * LBO) >> 4; del += (2 * LBO) >> 4;
+                            dwh += 2; dwl += 2; deh += 2; del += 2;      // next k-step: 32 bytes along the swizzled row
                         }
                         umma_commit(&hid_done[eb]);
                         ++kh;
                     }
                     progressed = true;
+                    WS_MARK(1);
                 }
                 if (km < kh && km < end && mbar_test(&h_full[km & 1], (km >> 1) & 1) && mbar_test(&f_full[km & 1], (km >> 1) & 1)) {
                     asm volatile("fence.acq_rel.cta;" ::: "memory");
                     const int b = km & 1;
                     const int4 ctl = ictl_m[b];          // (flags, item_seq, n)
                     const int acc = ctl.y & 1;
+                    WS_MARK(0);
                     if (ctl.x & 1) mbar_wait_ws(&acc_empty[acc], ((ctl.y >> 1) & 1) ^ 1);   // the epilogue of item_seq - 2 has drained it
+                    WS_MARK(2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t dacc = tmem_base + (uint32_t)(acc * ACC_COLS);
                     const uint32_t acc0 = (ctl.x & 1) ? 0u : 1u;
@@ -570,7 +621,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     mma_tf32(dacc, hh, fl, idesc, 1u);
                     mma_tf32(dacc, hl, fh, idesc, 1u);
                     if (((ctl.z + 7) >> 3) > 1) {
-                        const uint64_t ks = (uint64_t)((2 * LBO) >> 4);
+                        const uint64_t ks = 2;      // second k-step (edges 8-15): 32 bytes along the swizzled row
                         mma_tf32(dacc, hh + ks, fh + ks, idesc, 1u);
                         mma_tf32(dacc, hh + ks, fl + ks, idesc, 1u);
                         mma_tf32(dacc, hl + ks, fh + ks, idesc, 1u);
@@ -581,6 +632,7 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
                     last_seq = ctl.y;
                     ++km;
                     progressed = true;
+                    WS_MARK(3);
                 }
                 if (progressed) t0 = clock64();
                 else if (clock64() - t0 > 6000000000ll) __trap();      // bounded: ~3 s without progress
@@ -593,16 +645,23 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             idesc_ring[seq % NI] = it;
             asm volatile("fence.acq_rel.cta;" ::: "memory");
             mbar_arrive(&acc_full[seq & 1]);
+#ifdef CB_PHASE_TIMING
+            wph[4] = km;
+#endif
+            WS_FLUSH(5);
         }
     } else {
         // =============================================================== E: epilogue (TMEM -> registers -> workspace)
         const int lg = warp & 3;                    // warps 16..19 are lane groups 0..3
         const int j = lg * 32 + lane;
         const int c_lo = 0, c_hi = NRP;        // one warp per lane group: all f-row columns
+        WS_T0();
 #pragma unroll 1
         for (int item_seq = 0;; ++item_seq) {
             const int acc = item_seq & 1;
+            WS_MARK(1);
             mbar_wait_ws(&acc_full[acc], (item_seq >> 1) & 1);
+            WS_MARK(0);
             asm volatile("fence.acq_rel.cta;" ::: "memory");
             const ItemDesc it = idesc_ring[item_seq % NI];
             if (!it.valid) break;
@@ -646,7 +705,11 @@ tp_accumulate_ws_kernel(const __grid_constant__ cb_tp_conv_args a, int n_items) 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
+#ifdef CB_PHASE_TIMING
+            wph[2] += 1;
+#endif
         }
+        if (warp == F_WARPS + H_WARPS && lane == 0) WS_FLUSH(6);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -458,6 +458,7 @@ constexpr int ITEM_BLOCK = 1;   // consecutive (node, slot) items dealt to a per
 struct FRowCtx {
     const float* xs; const float* shs; const cb_tp_term* terms_s; unsigned char* Fhi; unsigned char* Flo;
     int dxp, S, n, nq, tb0, te0, rbase;
+    int e4_stride = LBO, e4_xor = 0;   // 16-byte chunk j of a row lands at rbase + (j ^ e4_xor) * e4_stride (swizzled tiles: stride 16, xor = row bits)
 };
 
 // F^T tile row of one thread: F[r][e] = sum_t coef_t * x[col e][xi_t] * sh_e[si_t] for the chunk's edges, hi/lo split,
@@ -496,15 +497,16 @@ __device__ __forceinline__ float f_row(const FRowCtx& c, const int (&t_xi)[MAXT]
         split_tf32_trunc(v[1], hi.y, lo.y);
         split_tf32_trunc(v[2], hi.z, lo.z);
         split_tf32_trunc(v[3], hi.w, lo.w);
-        *reinterpret_cast<float4*>(c.Fhi + c.rbase + e4 * LBO) = hi;   // 4 consecutive edges = one 16-byte core-matrix row
-        *reinterpret_cast<float4*>(c.Flo + c.rbase + e4 * LBO) = lo;
+        const int coff = c.rbase + (e4 ^ c.e4_xor) * c.e4_stride;
+        *reinterpret_cast<float4*>(c.Fhi + coff) = hi;   // 4 consecutive edges = one 16-byte chunk of the operand row
+        *reinterpret_cast<float4*>(c.Flo + coff) = lo;
         total += (v[0] + v[1]) + (v[2] + v[3]);
     }
     return total;
 }
 
 #ifdef CB_PHASE_TIMING
-__device__ unsigned long long cb_dbg_phase[2][12];
+__device__ unsigned long long cb_dbg_phase[8][12];
 #define PH_MARK(k) do { if (ph_on) { const long long t_ = clock64(); ph[k] += t_ - ph_t; ph_t = t_; } } while (0)
 #else
 #define PH_MARK(k) do { } while (0)
@@ -1520,9 +1522,9 @@ int launch_accumulate(const cb_tp_conv_args* a, int items, cudaStream_t st) {
 #ifdef CB_PHASE_TIMING
 extern "C" int cb_debug_phases(unsigned long long* out, int reset) {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, tc::cb_dbg_phase, sizeof(unsigned long long) * 24);
+    cudaMemcpyFromSymbol(out, tc::cb_dbg_phase, sizeof(unsigned long long) * 96);
     if (reset) {
-        unsigned long long z[24] = {0};
+        unsigned long long z[96] = {0};
         cudaMemcpyToSymbol(tc::cb_dbg_phase, z, sizeof(z));
     }
     return 0;
@@ -1579,7 +1581,7 @@ extern "C" int cb_tp_conv_forward(const cb_tp_conv_args* a, void* stream) {
         if (a->accum_mode == 4) {
             // warp-specialised kernel (tp_accumulate_ws.cuh): transposed accumulator, 1 CTA per SM, 512 TMEM columns
             const tc::ws::LayoutWS LW = tc::ws::make_layout_ws(R, a->n_terms, a->ne, a->d_in, a->S, H);
-            ws_ok = R <= tc::ws::ACC_COLS && H % 32 == 0 && H <= 128 && a->ne % 8 == 0 && a->d_in % 2 == 0 && LW.total <= 225 * 1024;
+            ws_ok = R <= tc::ws::ACC_COLS && H % 32 == 0 && H <= 128 && a->ne == 32 && a->d_in % 2 == 0 && LW.total <= 225 * 1024;   // ne = 32: 128-byte swizzled rows
             if (ws_ok) {
                 const size_t smem = (size_t)LW.total;
                 cudaError_t e = cudaFuncSetAttribute(tc::ws::tp_accumulate_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -27,7 +27,7 @@ ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
 # 1 = fp32 FFMA register tiles (kept for shapes outside the UMMA tile limits and for A/B measurements)
 ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "3"))
 FOLD_E_POST = True            # fold W1e.e_post[graph] into the node projection on the host (tests switch it off to cover the kernel path)
-TC_TRANSFORM = os.environ.get("CB200_TC_TRANSFORM", "1") != "0"   # tcgen05 transform kernel for big launches (FFMA kernel otherwise)
+TC_TRANSFORM = os.environ.get("CB200_TC_TRANSFORM", "0") != "0"   # experimental tcgen05 transform kernel (measured 3x slower than the FFMA kernel: DESIGN.md)
 DEBUG_KEEP_WORKSPACE = None   # tests may set this to a list to inspect the K3 accumulators
 WORKSPACE_BYTES = int(os.environ.get("CB200_WORKSPACE_MB", str(16 << 10))) << 20  # cap on the K3 accumulator workspace (180 GB of HBM3e per GPU); larger layers run in node chunks
 
