@@ -25,7 +25,7 @@ ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
 # accumulate kernel of K3: 3 = tcgen05 3xTF32 UMMA with the TRANSPOSED TMEM accumulator (default; layers with more than 240
 # f-rows -- the lmax-2 confidence layers -- automatically use 2); 2 = tcgen05 with the row-major accumulator;
 # 1 = fp32 FFMA register tiles (kept for shapes outside the UMMA tile limits and for A/B measurements)
-ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "3"))
+ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "4"))
 FOLD_E_POST = True            # fold W1e.e_post[graph] into the node projection on the host (tests switch it off to cover the kernel path)
 TC_TRANSFORM = os.environ.get("CB200_TC_TRANSFORM", "0") != "0"   # experimental tcgen05 transform kernel (measured 3x slower than the FFMA kernel: DESIGN.md)
 DEBUG_KEEP_WORKSPACE = None   # tests may set this to a list to inspect the K3 accumulators
