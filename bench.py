@@ -200,8 +200,8 @@ def workload_config(confidence):
 
 # ----------------------------------------------------------------------------------------- cb200 arm
 # dram__bytes_read.sum + dram__bytes_write.sum of the two K3 kernels for the 74->74 conv layer of the bench workload
-# (ncu --set full, profiles/r1/k3_ncu_summary.txt); refreshed whenever the kernels change
-K3_DRAM_BYTES_PER_CALL = 4.36e9   # 2.24 GB accumulate (2.06 GB written) + 2.12 GB transform (2.10 GB read), dead-output gate active
+# (ncu --set full, profiles/r2/k3_ncu_summary_final.txt); refreshed whenever the kernels change
+K3_DRAM_BYTES_PER_CALL = 4.21e9   # accumulate 0.207 GB read + 1.994 GB written, transform 1.987 GB read + 0.020 GB written
 
 
 class TpTimer:
@@ -400,8 +400,8 @@ def run_cb200(opts):
             out["roofline"] = {"bound": "tensor", "achieved": tf_ref, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_ref / peak_tf,
                                "traffic": K3_DRAM_BYTES_PER_CALL,
                                "traffic_note": "ncu dram read+write bytes of one K3 call of the 74->74 conv layer (accumulate + transform), "
-                                               "profiles/r1; dominated by the accumulator workspace written once and read once",
-                               "kernel": "K3 = tp_accumulate_tc_kernel (tcgen05 3xTF32) + tp_transform_kernel, all launches of the timed region",
+                                               "profiles/r2/k3_ncu_summary_final.txt; the accumulator workspace written once and read once",
+                               "kernel": "K3 = tp_accumulate_ws_kernel (warp-specialised, tcgen05 3xTF32) + tp_transform_kernel (fp32 FFMA2), all launches of the timed region",
                                "peak_source": peaks["source"] + ", dense bf16 sustained; 3xTF32 emulation can reach at most 1/6 of it",
                                "launches": tp["launches"], "avg_launch_ms": tp["ms"] / tp["launches"],
                                # K3 time per step (CUDA events of the hook pass) over the step time of the un-hooked timed pass
