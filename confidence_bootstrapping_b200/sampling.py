@@ -8,10 +8,12 @@ arithmetic of sampling.py:119-141 is folded into the K4 launch as scalar coeffic
 """
 from __future__ import annotations
 
+import collections
 import contextlib
 import copy
 import os
 import warnings
+import weakref
 
 import numpy as np
 import torch
@@ -157,12 +159,17 @@ def _inference_mode(*models):
                               "dropout on, batch-statistic BatchNorm); cb200 samples in eval mode and restores train mode afterwards")
                 _warned_train_mode = True
             m.eval()
-        # folded weights (W2a, projections, BatchNorm affine) are rebuilt per call: in-place `.data` writes
-        # (ExponentialMovingAverage.copy_to / restore between sampling calls) do not bump tensor versions
-        for sub in m.modules():
-            inv = getattr(sub, "invalidate_caches", None)
-            if inv is not None:
-                inv()
+        # folded weights (W2a, projections, BatchNorm affine) must follow in-place `.data` writes, which do not bump tensor
+        # versions (ExponentialMovingAverage.copy_to / restore between sampling calls): a per-tensor (L1, L2) signature of
+        # every parameter and buffer is compared with the one the caches were built under, and they are dropped when it moved
+        sig = _weights_signature(m)
+        old = getattr(m, "_cb200_weights_sig", None)
+        if old is None or old[0] != sig[0] or not torch.equal(old[1], sig[1]):
+            for sub in m.modules():
+                inv = getattr(sub, "invalidate_caches", None)
+                if inv is not None:
+                    inv()
+            object.__setattr__(m, "_cb200_weights_sig", sig)
     try:
         yield
     finally:
@@ -171,7 +178,26 @@ def _inference_mode(*models):
                 m.train(True)
 
 
+def _weights_signature(model):
+    """(data pointers, [L2 norms | L1 norms] of every parameter and floating buffer) -- two multi-tensor launches and one
+    small D2H per sampling call."""
+    ts = [p.detach() for p in model.parameters()] + [b.detach() for b in model.buffers() if b.is_floating_point()]
+    ts = [t for t in ts if t.numel() > 0]
+    if not ts:
+        return (), torch.zeros(0, dtype=torch.float64)
+    ptrs = tuple(t.data_ptr() for t in ts)
+    fl = [t.float() if t.dtype != torch.float32 else t for t in ts]
+    sig = torch.stack(list(torch._foreach_norm(fl, 2)) + list(torch._foreach_norm(fl, 1))).double().cpu()
+    return ptrs, sig
+
+
 USE_CUDA_GRAPH = os.environ.get("CB200_CUDA_GRAPH", "1") != "0"
+# Step graphs of recent batches, keyed on (complex fingerprint, model, weights epoch, batch / schedule parameters): a later batch
+# of the SAME complex (inference.py samples 40 poses in batches of 10; finetune_train.py re-samples every complex each epoch)
+# copies its poses into the captured batch and replays all steps -- no eager first step, no capture.
+GRAPH_CACHE_SIZE = int(os.environ.get("CB200_GRAPH_CACHE", "2"))
+_graph_cache = collections.OrderedDict()
+graph_cache_hits = 0
 _graph_warned = False
 _graph_pools = {}      # device index -> memory-pool handle shared by every step graph captured on that device
 
@@ -292,6 +318,29 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
         return zs
 
     graph, vals, z_static, tor_shape, graph_launches, step_table = None, None, None, None, 0, None
+    # ---- a step graph captured for an earlier batch of the same complex (same model, weights, batch and schedule)?
+    cache_key, reused = None, None
+    fp = batch._g.get("_fingerprint") if hasattr(batch, "_g") else None
+    if use_graph and fp is not None and GRAPH_CACHE_SIZE > 0 and isinstance(model, torch.nn.Module):
+        from . import tensor_layers
+        wv = (tensor_layers.CACHE_EPOCH, sum(p._version for p in model.parameters()), sum(x._version for x in model.buffers()))
+        sch = tuple(tuple(float(v) for v in sc) for sc in (tr_schedule, rot_schedule, tor_schedule))
+        cache_key = (fp, id(model), wv, b, nb, int(inference_steps), sch, bool(no_random), bool(ode), bool(no_final_step_noise),
+                     tuple(float(v) for v in temp_sampling), tuple(float(v) for v in temp_psi), float(temp_sigma_data), no_torsion,
+                     t_schedule is None, torch.device(device).index, tuple(pos.shape))
+        for k in [k for k in _graph_cache if k[1] == id(model) and k[2] != wv]:
+            del _graph_cache[k]          # captured under other weights: its derived-weight tensors are gone
+        reused = _graph_cache.get(cache_key)
+        if reused is not None and reused["model"]() is not model:      # id() of a dead model re-used by a new one
+            del _graph_cache[cache_key]
+            reused = None
+    if reused is not None:
+        global graph_cache_hits
+        graph_cache_hits += 1
+        _graph_cache.move_to_end(cache_key)
+        graph, vals, z_static, tor_shape, graph_launches, step_table = (reused[k] for k in ("graph", "vals", "z_static", "tor_shape",
+                                                                                             "graph_launches", "step_table"))
+        reused["pos"].copy_(pos)
     for t_idx in range(inference_steps):
         (t_tr, t_rot, t_tor), coeffs, noisy = scal(t_idx)
         if graph is None:
@@ -329,17 +378,59 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
         vals.copy_(step_table[t_idx])
         zs = draw(noisy, tor_shape)
         for zb, z in zip(z_static, zs):
-            if (zb is None) != (z is None):
-                raise RuntimeError("cb200: noise pattern changed between graph replays")
+            if zb is None and z is not None:
+                raise RuntimeError("cb200: a noise term appeared after the step graph was captured without it")
             if zb is not None:
-                zb.copy_(z)
+                if z is None:
+                    zb.zero_()       # noiseless step (no_final_step_noise): the captured c_noise * z term adds exactly zero
+                else:
+                    zb.copy_(z)
         graph.replay()
         _lib.launch_count += graph_launches
     if graph is not None:
-        batch.cb200_step = None
+        if reused is not None:
+            pos = reused["pos"].clone()          # the captured buffer belongs to the cache entry
+            batch["ligand"].pos = pos
+        elif cache_key is not None:
+            # keep the graph for later batches of this complex: the entry owns the captured batch (every tensor the graph reads)
+            # and the pose buffer the graph updates in place; the caller gets a copy
+            _graph_cache[cache_key] = dict(graph=graph, vals=vals, z_static=z_static, tor_shape=tor_shape, graph_launches=graph_launches,
+                                           step_table=step_table, pos=pos, topo=topo, keep=_tensor_refs(batch), model=weakref.ref(model))
+            while len(_graph_cache) > GRAPH_CACHE_SIZE:
+                _graph_cache.popitem(last=False)
+            pos = pos.clone()
+            batch["ligand"].pos = pos
+        if hasattr(batch, "cb200_step"):
+            batch.cb200_step = None
         set_time(batch, None, tr_schedule[inference_steps - 1], rot_schedule[inference_steps - 1], tor_schedule[inference_steps - 1], b,
                  all_atoms, asyncronous_noise_schedule, device)
     return pos
+
+
+def _tensor_refs(batch):
+    """Every tensor reachable from the batch's stores and graph-level attributes (static caches included): a cached step
+    graph reads them by address, so the cache entry keeps them alive whatever the caller does with the batch object."""
+    out, seen = [], set()
+
+    def walk(v, depth=0):
+        if torch.is_tensor(v):
+            out.append(v)
+        elif depth < 6 and id(v) not in seen:
+            seen.add(id(v))
+            if isinstance(v, dict):
+                for x in v.values():
+                    walk(x, depth + 1)
+            elif isinstance(v, (list, tuple)):
+                for x in v:
+                    walk(x, depth + 1)
+            elif hasattr(v, "__dict__") and not isinstance(v, (torch.nn.Module, type)):
+                for x in vars(v).values():
+                    walk(x, depth + 1)
+
+    for st in batch._stores.values():
+        walk(st._d)
+    walk(batch._g)
+    return out
 
 
 def _capture_step(batch, model, pos, topo, b, nb, tor_shape, no_torsion, noisy, device):

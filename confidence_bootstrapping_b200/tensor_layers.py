@@ -26,6 +26,15 @@ ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU}
 # f-rows -- the lmax-2 confidence layers -- automatically use 2); 2 = tcgen05 with the row-major accumulator;
 # 1 = fp32 FFMA register tiles (kept for shapes outside the UMMA tile limits and for A/B measurements)
 ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "4"))
+# bumped whenever a layer drops tensors derived from its weights: captured CUDA graphs hold pointers to those tensors and
+# are only replayed under the epoch they were captured in (sampling._graph_cache)
+CACHE_EPOCH = 0
+
+
+def _bump_epoch():
+    global CACHE_EPOCH
+    CACHE_EPOCH += 1
+
 FOLD_E_POST = True            # fold W1e.e_post[graph] into the node projection on the host (tests switch it off to cover the kernel path)
 TC_TRANSFORM = os.environ.get("CB200_TC_TRANSFORM", "0") != "0"   # experimental tcgen05 transform kernel (measured 3x slower than the FFMA kernel: DESIGN.md)
 DEBUG_KEEP_WORKSPACE = None   # tests may set this to a list to inspect the K3 accumulators
@@ -76,13 +85,14 @@ class EquivariantBatchNorm(nn.Module):
         """Forget the folded (scale, shift).  The cache key (data_ptr, _version) does not see writes through
         `param.data.copy_()` (the reference's ExponentialMovingAverage.copy_to / restore, utils/utils.py:353-392)."""
         self._affine_cache = None
+        _bump_epoch()
 
     def _apply(self, fn, *a, **kw):
-        self._affine_cache = None
+        self.invalidate_caches()
         return super()._apply(fn, *a, **kw)
 
     def _load_from_state_dict(self, *a, **kw):
-        self._affine_cache = None
+        self.invalidate_caches()
         return super()._load_from_state_dict(*a, **kw)
 
     def affine(self):
@@ -175,15 +185,18 @@ class TensorProductConvLayer(nn.Module):
         self._w2t_cache.clear()
         self._proj_cache.clear()
         self._param_cache.clear()
+        _bump_epoch()
         if self.batch_norm is not None:
             self.batch_norm.invalidate_caches()
 
     def _apply(self, fn, *a, **kw):
         self._w2a_cache.clear(); self._w2t_cache.clear(); self._proj_cache.clear(); self._param_cache.clear()
+        _bump_epoch()
         return super()._apply(fn, *a, **kw)
 
     def _load_from_state_dict(self, *a, **kw):
         self._w2a_cache.clear(); self._w2t_cache.clear(); self._proj_cache.clear(); self._param_cache.clear()
+        _bump_epoch()
         return super()._load_from_state_dict(*a, **kw)
 
     def train(self, mode=True):

@@ -297,6 +297,58 @@ def test_sampling_is_bit_reproducible():
 
 
 @pytest.mark.gpu
+def test_step_graph_reuse_is_bit_identical_and_follows_the_weights():
+    """A later batch of the same complex replays the cached step graph of the first one (no eager step, no capture): same
+    bits as a run with the cache off, and a weight change between the calls is honoured (no stale graph)."""
+    from confidence_bootstrapping_b200 import sampling as smp
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule
+    from confidence_bootstrapping_b200.sampling import randomize_position, sampling
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    args = score_model_args()
+    model, t2s, _ = _build(args, seed=4)
+    g = Batch.from_data_list([make_complex(79, 60, 12, all_atoms=False)])
+    sched = get_t_schedule("expbeta", 6, 1, 1)
+
+    def run(seed, cache):
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        dl = [copy.deepcopy(g) for _ in range(4)]
+        randomize_position(dl, False, False, args.tr_sigma_max)
+        old = smp.GRAPH_CACHE_SIZE
+        smp.GRAPH_CACHE_SIZE = 2 if cache else 0
+        try:
+            with injected_noise(seed=seed + 100):
+                out, _ = sampling(data_list=dl, model=model, inference_steps=6, tr_schedule=sched, rot_schedule=sched, tor_schedule=sched,
+                                  device=torch.device("cuda"), t_to_sigma=t2s, model_args=args, batch_size=4, no_final_step_noise=True)
+        finally:
+            smp.GRAPH_CACHE_SIZE = old
+        return torch.stack([d["ligand"].pos for d in out]).cpu()
+
+    smp._graph_cache.clear()
+    ref = [run(s, cache=False) for s in (1, 2, 3)]
+    h0 = smp.graph_cache_hits
+    got = [run(s, cache=True) for s in (1, 2, 3)]
+    assert smp.graph_cache_hits == h0 + 2                      # the first call captures, the next two replay
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    # EMA-style in-place weight change: the cached graph (which points at the old folded weights) must not be replayed
+    w = max(model.conv_layers[1].parameters(), key=lambda p: p.numel())          # a second-Linear weight of the radial MLP
+    saved = w.data.clone()
+    w.data.mul_(1.5)
+    try:
+        moved_ref = run(2, cache=False)
+        h1 = smp.graph_cache_hits
+        moved = run(2, cache=True)
+        assert smp.graph_cache_hits == h1
+        assert torch.equal(moved, moved_ref) and not torch.equal(moved, ref[1])
+    finally:
+        w.data.copy_(saved)
+    smp._graph_cache.clear()
+
+
+@pytest.mark.gpu
 def test_dead_output_gates_do_not_change_the_scores():
     """The per-layer receptor keep masks (score_model._dead_output_gates) only skip rows nobody reads: the scores are
     bit-identical with and without them."""

@@ -384,3 +384,52 @@ def test_select_confident_and_plain_rmsd():
     pos = torch.zeros(2, 4, 3)
     pos[1, :, 0] = 2.0
     assert torch.allclose(plain_rmsd(pos, torch.zeros(4, 3)), torch.tensor([0.0, 2.0]))
+
+
+def test_collate_fingerprint_ignores_the_pose_only():
+    """The CUDA-graph cache of reverse_diffusion is keyed on this: same complex + different poses -> same hash."""
+    import copy
+    g = make_complex(11, 30, 9, all_atoms=False)
+    dl = [copy.deepcopy(g) for _ in range(3)]
+    for i, d in enumerate(dl):
+        d["ligand"].pos = d["ligand"].pos + float(i)
+    fp = Batch.from_data_list(dl, device="cpu")._g["_fingerprint"]
+    assert fp is not None
+    dl2 = [copy.deepcopy(g) for _ in range(3)]
+    for i, d in enumerate(dl2):
+        d["ligand"].pos = d["ligand"].pos * 2.0 - float(i)
+    assert Batch.from_data_list(dl2, device="cpu")._g["_fingerprint"] == fp
+    # another complex, another number of copies, a changed receptor coordinate: different hashes
+    other = [copy.deepcopy(make_complex(12, 30, 9, all_atoms=False)) for _ in range(3)]
+    assert Batch.from_data_list(other, device="cpu")._g["_fingerprint"] != fp
+    assert Batch.from_data_list(dl[:2], device="cpu")._g["_fingerprint"] != fp
+    dl3 = [copy.deepcopy(g) for _ in range(3)]
+    for d in dl3:
+        d["receptor"].pos[0, 0] += 1.0
+    assert Batch.from_data_list(dl3, device="cpu")._g["_fingerprint"] != fp
+    # copies that differ in more than the pose, and the host collate, carry no fingerprint
+    dl3[1]["receptor"].pos[0, 0] += 1.0
+    assert Batch.from_data_list(dl3, device="cpu")._g["_fingerprint"] is None
+    assert Batch.from_data_list(dl)._g.get("_fingerprint") is None
+
+
+def test_sampling_refreshes_derived_weights_only_when_the_weights_moved():
+    """_inference_mode compares a per-tensor norm signature: unchanged weights keep the folded tensors (and the cached step
+    graphs), an EMA-style `.data.copy_()` drops them."""
+    from confidence_bootstrapping_b200 import sampling as smp, tensor_layers as tl
+    from confidence_bootstrapping_b200.tensor_layers import TensorProductConvLayer
+    torch.manual_seed(0)
+    layer = TensorProductConvLayer("8x0e + 2x1o", "1x0e + 1x1o", "8x0e + 2x1o", 24, hidden_features=24, faster=True).eval()
+    with smp._inference_mode(layer):
+        w2a = layer._w2a(0)
+    e0 = tl.CACHE_EPOCH
+    with smp._inference_mode(layer):
+        assert layer._w2a(0) is w2a and tl.CACHE_EPOCH == e0          # nothing moved: same tensor object, same epoch
+    layer.fc[3].weight.data.copy_(layer.fc[3].weight.data * 2)
+    with smp._inference_mode(layer):
+        assert tl.CACHE_EPOCH > e0
+        assert torch.allclose(layer._w2a(0)[:, :24], 2 * w2a[:, :24])
+    e1 = tl.CACHE_EPOCH
+    layer.batch_norm.running_var.data.mul_(4.0)                          # buffers count too
+    with smp._inference_mode(layer):
+        assert tl.CACHE_EPOCH > e1
