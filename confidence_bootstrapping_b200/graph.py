@@ -59,10 +59,13 @@ def radius_edges(x, x_ptr, y, y_batch, r, max_neighbors, cap, cutoff=None, exclu
     rowptr = torch.empty(n_y + 1, dtype=torch.int32, device=dev)
     row = torch.zeros(max(cap, 1), dtype=torch.int32, device=dev)
     col = torch.zeros(max(cap, 1), dtype=torch.int32, device=dev)
-    if n_y > 0:
+    search = n_y > 0 and x.shape[0] > 0          # an empty candidate set (e.g. crop_beyond removed every residue): no edges
+    if search:
         _lib.radius_count(x, x_ptr, y, y_batch, cutoff, float(r), max_neighbors, exclude_self, count)
+    else:
+        count.zero_()
     _lib.exclusive_scan(count[:n_y], rowptr, _scratch(dev))
-    if n_y > 0:
+    if search:
         _lib.radius_fill(x, x_ptr, y, y_batch, cutoff, float(r), max_neighbors, exclude_self, rowptr, row, col)
     return EdgeList(rowptr, row, col, cap, n_y)
 
@@ -80,10 +83,13 @@ def radius_edges_transposed(x, x_batch, y, y_ptr, r, cap, cutoff=None, exclude_s
     col = torch.zeros(max(cap, 1), dtype=torch.int32, device=dev)
     kr = kept.rowptr if kept is not None else None
     kc = kept.col if kept is not None else None
-    if n_x > 0:
+    search = n_x > 0 and y.shape[0] > 0
+    if search:
         _lib.radius_count_t(x, x_batch, y, y_ptr, cutoff, float(r), exclude_self, kr, kc, count)
+    else:
+        count.zero_()
     _lib.exclusive_scan(count[:n_x], rowptr, _scratch(dev))
-    if n_x > 0:
+    if search:
         _lib.radius_fill_t(x, x_batch, y, y_ptr, cutoff, float(r), exclude_self, kr, kc, rowptr, row, col)
     return EdgeList(rowptr, row, col, cap, n_x)
 

@@ -240,6 +240,41 @@ def test_all_atom_model_vs_oracle(mode):
             assert rel_err(a, b) < 1e-4
 
 
+@pytest.mark.parametrize("far", ["one", "all"])
+def test_confidence_model_when_crop_beyond_removes_a_whole_receptor(far):
+    """Edge case of the filtering leg (sampling.py:226-233 -> utils.py:395-420): a pose that drifted away from the pocket leaves
+    its graph with NO receptor residue / atom after crop_beyond -- for one graph of the batch, or for all of them (empty
+    receptor tensors).  The device path must score such batches like the reference arithmetic does (oracle), not fail."""
+    from confidence_bootstrapping_b200.configs import confidence_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import set_time
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    from confidence_bootstrapping_b200.utils import crop_beyond, get_model
+    dev = torch.device("cuda")
+    args = confidence_model_args()
+    torch.manual_seed(5)
+    model = get_model(args, dev, t_to_sigma=None, no_parallel=True, confidence_mode=True)
+    randomize_norm_stats(model, seed=6)
+    model.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    hp = om.hyper_from_args(args, confidence_mode=True)
+    graphs = [make_complex(95 + i, 45 + 10 * i, 9 + 3 * i, all_atoms=True) for i in range(2)]
+    for i, g in enumerate(graphs):
+        if far == "all" or i == 1:
+            g["ligand"].pos = g["ligand"].pos + 500.0
+    gpu = crop_beyond(Batch.from_data_list(copy.deepcopy(graphs)).to(dev), args.crop_beyond, True)
+    assert gpu["receptor"].num_nodes == (0 if far == "all" else gpu["receptor"].num_nodes) and (far == "one" or gpu["atom"].num_nodes == 0)
+    set_time(gpu, 0, 0, 0, 0, 2, True, False, dev)
+    with torch.no_grad():
+        conf = model(gpu)[0]
+    assert conf.shape[0] == 2 and bool(torch.isfinite(conf).all())
+    cpu = Batch.from_data_list([osamp.crop_beyond(copy.deepcopy(g), args.crop_beyond, True) for g in graphs])
+    osamp.set_time(cpu, 0, 0, 0, 2, all_atoms=True)
+    with torch.no_grad():
+        want = om.aa_forward(sd, hp, cpu, None, None, None)[0]
+    assert torch.allclose(conf.cpu(), want, atol=1e-4)
+
+
 @pytest.mark.gpu
 def test_e_post_fold_matches_kernel_path():
     """The per-graph edge-embedding offset (rec_sigma_emb) folded into the node projection on the host equals the
