@@ -182,44 +182,19 @@ def _cat0(vals, device, rep_out=None):
     return out.to(device, non_blocking=True)
 
 
-def _fingerprint(first, n, skip=(("ligand", "pos"),)):
-    """Content hash of everything in one graph except the ligand pose (host tensors / arrays only): two batches built from
-    N copies of the same complex get the same value, whatever their poses.  sampling.reverse_diffusion keys its CUDA-graph
-    cache on it."""
-    import hashlib
-    h = hashlib.blake2b(digest_size=16)
-    h.update(str(n).encode())
-
-    def feed(tag, v):
-        if torch.is_tensor(v):
-            if v.device.type != "cpu":
-                return False
-            h.update(f"{tag}|{tuple(v.shape)}|{v.dtype}".encode())
-            h.update(v.contiguous().view(torch.uint8).numpy().tobytes() if v.numel() else b"")
-        elif isinstance(v, np.ndarray):
-            h.update(f"{tag}|{v.shape}|{v.dtype}".encode())
-            h.update(np.ascontiguousarray(v).tobytes())
-        elif isinstance(v, (str, int, float, bool, type(None))):
-            h.update(f"{tag}|{v!r}".encode())
-        elif isinstance(v, (list, tuple)):
-            for i, x in enumerate(v):
-                if not feed(f"{tag}[{i}]", x):
-                    return False
-        else:
-            h.update(f"{tag}|{type(v).__name__}".encode())
-        return True
-
-    for key in list(first.node_types) + list(first.edge_types):
-        st = first[key]
-        for k in sorted(st.keys()):
-            if (key, k) in skip:
-                continue
-            if not feed(f"{key}.{k}", st._d[k]):
-                return None
-    for k in sorted(first._g.keys()):
-        if not k.startswith("_") and not feed(f"g.{k}", first._g[k]):
-            return None
-    return h.hexdigest()
+def _static_signature(batch, skip=(("ligand", "pos"),)):
+    """(store, attribute, shape, dtype) of every tensor of a collated batch except the ligand pose -- no data is read.
+    sampling.reverse_diffusion uses it as the cheap first key of its step-graph cache (a match is then verified element by
+    element on the device)."""
+    sig = []
+    for key, st in batch._stores.items():
+        for k, v in st._d.items():
+            if torch.is_tensor(v) and (key, k) not in skip:
+                sig.append((str(key), k, tuple(v.shape), str(v.dtype)))
+    for k, v in batch._g.items():
+        if torch.is_tensor(v) and not k.startswith("_"):
+            sig.append(("", k, tuple(v.shape), str(v.dtype)))
+    return tuple(sorted(sig))
 
 
 class Batch(HeteroData):
@@ -276,13 +251,12 @@ class Batch(HeteroData):
                     slices[et][k] = [0] + list(np.cumsum([v.shape[0] for v in vals]))
                 else:
                     st._d[k] = vals
-        g_flags: List[bool] = []
         for k in first._g.keys():
             if k.startswith("_"):
                 continue
             vals = [d._g[k] for d in data_list]
             if _is_cat_tensor(vals[0]):
-                b._g[k] = _cat0(vals, device, g_flags)
+                b._g[k] = _cat0(vals, device)
             elif torch.is_tensor(vals[0]):
                 b._g[k] = torch.stack(vals, 0)
                 if device is not None:
@@ -299,15 +273,8 @@ class Batch(HeteroData):
         b._g["_num_graphs"] = n
         b._g["_slices"] = slices
         b._g["_offs"] = offs
-        # N copies of ONE complex that differ in the ligand pose only (what inference.py / finetune_train.py sample): a content
-        # hash of the shared part lets reverse_diffusion re-use the captured step graph of an earlier batch of the same complex
-        b._g["_fingerprint"] = None
-        if device is not None and n > 1:
-            lig_keys = [k for k in first["ligand"].keys() if _is_cat_tensor(first["ligand"]._d[k])] if "ligand" in first.node_types else []
-            ok = all(all(f) for key, f in rep_flags.items() if key != "ligand") and all(g_flags)
-            ok = ok and all(f for k, f in zip(lig_keys, rep_flags.get("ligand", [])) if k != "pos")
-            if ok:
-                b._g["_fingerprint"] = _fingerprint(first, n)
+        # shape-level signature of everything but the ligand pose (sampling.reverse_diffusion: step-graph cache key)
+        b._g["_static_sig"] = _static_signature(b) if device is not None else None
         return b
 
     def _rebuild_slices(self):

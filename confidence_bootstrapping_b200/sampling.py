@@ -195,7 +195,10 @@ USE_CUDA_GRAPH = os.environ.get("CB200_CUDA_GRAPH", "1") != "0"
 # Step graphs of recent batches, keyed on (complex fingerprint, model, weights epoch, batch / schedule parameters): a later batch
 # of the SAME complex (inference.py samples 40 poses in batches of 10; finetune_train.py re-samples every complex each epoch)
 # copies its poses into the captured batch and replays all steps -- no eager first step, no capture.
-GRAPH_CACHE_SIZE = int(os.environ.get("CB200_GRAPH_CACHE", "2"))
+# At most ONE step graph is alive per process: a miss drops the cached graph BEFORE the new batch's eager step, so its private
+# pool (the K3 workspaces: up to 16 GiB per layer for 1000-residue complexes) is free for the new capture.  (Two cached graphs
+# drove a mixed-size run -- BASELINE configs[3], N_r up to 1000 -- out of memory: 49 GiB in graph pools + fragmentation.)
+GRAPH_CACHE_SIZE = int(os.environ.get("CB200_GRAPH_CACHE", "1"))
 _graph_cache = collections.OrderedDict()
 graph_cache_hits = 0
 _graph_warned = False
@@ -320,7 +323,7 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
     graph, vals, z_static, tor_shape, graph_launches, step_table = None, None, None, None, 0, None
     # ---- a step graph captured for an earlier batch of the same complex (same model, weights, batch and schedule)?
     cache_key, reused = None, None
-    fp = batch._g.get("_fingerprint") if hasattr(batch, "_g") else None
+    fp = batch._g.get("_static_sig") if hasattr(batch, "_g") else None
     if use_graph and fp is not None and GRAPH_CACHE_SIZE > 0 and isinstance(model, torch.nn.Module):
         from . import tensor_layers
         wv = (tensor_layers.CACHE_EPOCH, sum(p._version for p in model.parameters()), sum(x._version for x in model.buffers()))
@@ -331,9 +334,13 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
         for k in [k for k in _graph_cache if k[1] == id(model) and k[2] != wv]:
             del _graph_cache[k]          # captured under other weights: its derived-weight tensors are gone
         reused = _graph_cache.get(cache_key)
-        if reused is not None and reused["model"]() is not model:      # id() of a dead model re-used by a new one
+        # same shapes is only a candidate: the graph is replayed when the model object is the captured one and every tensor of
+        # the batch except the pose (and the rotatable-bond masks the pose update was built from) equals the captured batch's
+        if reused is not None and (reused["model"]() is not model or not _same_static(batch, mask_rotate, reused)):
             del _graph_cache[cache_key]
             reused = None
+    if reused is None and use_graph and _graph_cache:
+        _graph_cache.clear()             # free the previous complex's graph pool before this batch allocates its own
     if reused is not None:
         global graph_cache_hits
         graph_cache_hits += 1
@@ -395,7 +402,8 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
             # keep the graph for later batches of this complex: the entry owns the captured batch (every tensor the graph reads)
             # and the pose buffer the graph updates in place; the caller gets a copy
             _graph_cache[cache_key] = dict(graph=graph, vals=vals, z_static=z_static, tor_shape=tor_shape, graph_launches=graph_launches,
-                                           step_table=step_table, pos=pos, topo=topo, keep=_tensor_refs(batch), model=weakref.ref(model))
+                                           step_table=step_table, pos=pos, topo=topo, keep=_tensor_refs(batch), model=weakref.ref(model),
+                                           static=_static_tensors(batch), mask_rotate=copy.deepcopy(mask_rotate))
             while len(_graph_cache) > GRAPH_CACHE_SIZE:
                 _graph_cache.popitem(last=False)
             pos = pos.clone()
@@ -405,6 +413,42 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
         set_time(batch, None, tr_schedule[inference_steps - 1], rot_schedule[inference_steps - 1], tor_schedule[inference_steps - 1], b,
                  all_atoms, asyncronous_noise_schedule, device)
     return pos
+
+
+def _static_tensors(batch):
+    """name -> tensor for the attributes listed in the batch's collate-time signature (data._static_signature): everything a
+    collated batch carries except the ligand pose; attributes the model or set_time added later are not part of it."""
+    names = {(k, a) for k, a, _, _ in (batch._g.get("_static_sig") or ())}
+    out = {}
+    for key, st in batch._stores.items():
+        for k, v in st._d.items():
+            if torch.is_tensor(v) and (str(key), k) in names:
+                out[(key, k)] = v
+    return out
+
+
+def _same_static(batch, mask_rotate, entry):
+    """Is `batch` the captured batch up to the ligand pose?  One device-side comparison per tensor, one host sync."""
+    mr0 = entry["mask_rotate"]
+    try:
+        if type(mr0) is not type(mask_rotate):
+            return False
+        if isinstance(mr0, (list, tuple)):
+            if len(mr0) != len(mask_rotate) or not all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(mr0, mask_rotate)):
+                return False
+        elif not np.array_equal(np.asarray(mr0), np.asarray(mask_rotate)):
+            return False
+    except Exception:
+        return False
+    flags = []
+    for (key, k), ref in entry["static"].items():
+        st = batch._stores.get(key)
+        v = st._d.get(k) if st is not None else None
+        if not torch.is_tensor(v) or v.shape != ref.shape or v.dtype != ref.dtype or v.device != ref.device:
+            return False
+        flags.append(torch.equal(v, ref) if v.numel() == 0 else (v == ref).all())
+    flags = [f for f in flags if torch.is_tensor(f)]
+    return bool(torch.stack(flags).all()) if flags else True
 
 
 def _tensor_refs(batch):

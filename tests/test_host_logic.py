@@ -386,31 +386,37 @@ def test_select_confident_and_plain_rmsd():
     assert torch.allclose(plain_rmsd(pos, torch.zeros(4, 3)), torch.tensor([0.0, 2.0]))
 
 
-def test_collate_fingerprint_ignores_the_pose_only():
-    """The CUDA-graph cache of reverse_diffusion is keyed on this: same complex + different poses -> same hash."""
+def test_step_graph_cache_key_ignores_the_pose_only():
+    """reverse_diffusion re-uses a captured step graph for a batch that equals the captured one up to the ligand pose:
+    shape-level signature from the collate (cheap candidate key) + element-wise check against the captured tensors."""
     import copy
+    from confidence_bootstrapping_b200 import sampling as smp
     g = make_complex(11, 30, 9, all_atoms=False)
-    dl = [copy.deepcopy(g) for _ in range(3)]
-    for i, d in enumerate(dl):
-        d["ligand"].pos = d["ligand"].pos + float(i)
-    fp = Batch.from_data_list(dl, device="cpu")._g["_fingerprint"]
-    assert fp is not None
-    dl2 = [copy.deepcopy(g) for _ in range(3)]
-    for i, d in enumerate(dl2):
-        d["ligand"].pos = d["ligand"].pos * 2.0 - float(i)
-    assert Batch.from_data_list(dl2, device="cpu")._g["_fingerprint"] == fp
-    # another complex, another number of copies, a changed receptor coordinate: different hashes
-    other = [copy.deepcopy(make_complex(12, 30, 9, all_atoms=False)) for _ in range(3)]
-    assert Batch.from_data_list(other, device="cpu")._g["_fingerprint"] != fp
-    assert Batch.from_data_list(dl[:2], device="cpu")._g["_fingerprint"] != fp
-    dl3 = [copy.deepcopy(g) for _ in range(3)]
-    for d in dl3:
-        d["receptor"].pos[0, 0] += 1.0
-    assert Batch.from_data_list(dl3, device="cpu")._g["_fingerprint"] != fp
-    # copies that differ in more than the pose, and the host collate, carry no fingerprint
-    dl3[1]["receptor"].pos[0, 0] += 1.0
-    assert Batch.from_data_list(dl3, device="cpu")._g["_fingerprint"] is None
-    assert Batch.from_data_list(dl)._g.get("_fingerprint") is None
+
+    def batch_of(graph, n, shift):
+        dl = [copy.deepcopy(graph) for _ in range(n)]
+        for i, d in enumerate(dl):
+            d["ligand"].pos = d["ligand"].pos * shift + float(i)
+        return Batch.from_data_list(dl, device="cpu"), smp._mask_rotate_of(dl[0])
+
+    b0, mr0 = batch_of(g, 3, 1.0)
+    sig = b0._g["_static_sig"]
+    assert sig is not None and not any(k == "pos" and "ligand" in key for key, k, _, _ in sig)
+    assert Batch.from_data_list([copy.deepcopy(g)])._g.get("_static_sig") is None          # host collate: no key
+    entry = dict(static=smp._static_tensors(b0), mask_rotate=copy.deepcopy(mr0))
+    assert ("ligand", "pos") not in entry["static"] and ("receptor", "pos") in entry["static"]
+    b1, mr1 = batch_of(g, 3, 2.0)                               # other poses, same complex
+    assert b1._g["_static_sig"] == sig and smp._same_static(b1, mr1, entry)
+    other = make_complex(12, 30, 9, all_atoms=False)            # same sizes, other complex: same shapes, different content
+    b2, mr2 = batch_of(other, 3, 1.0)
+    if b2._g["_static_sig"] == sig:
+        assert not smp._same_static(b2, mr2, entry)
+    b3, _ = batch_of(g, 2, 1.0)                                 # other number of copies
+    assert b3._g["_static_sig"] != sig
+    g4 = copy.deepcopy(g)
+    g4["receptor"].pos[0, 0] += 1.0                             # one moved residue
+    b4, mr4 = batch_of(g4, 3, 1.0)
+    assert b4._g["_static_sig"] == sig and not smp._same_static(b4, mr4, entry)
 
 
 def test_sampling_refreshes_derived_weights_only_when_the_weights_moved():
