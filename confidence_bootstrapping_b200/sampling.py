@@ -199,6 +199,10 @@ USE_CUDA_GRAPH = os.environ.get("CB200_CUDA_GRAPH", "1") != "0"
 # pool (the K3 workspaces: up to 16 GiB per layer for 1000-residue complexes) is free for the new capture.  (Two cached graphs
 # drove a mixed-size run -- BASELINE configs[3], N_r up to 1000 -- out of memory: 49 GiB in graph pools + fragmentation.)
 GRAPH_CACHE_SIZE = int(os.environ.get("CB200_GRAPH_CACHE", "1"))
+# Option: once a model has run one eager step under its current weights, later batches capture their step graph BEFORE step 0
+# (static tables built by model._static, no eager forward per batch).  Bit-identical (tests) but measured no faster -- the
+# eager step it saves overlapped the capture's host time anyway (configs[3]: 86 vs 91 poses/s, within noise) -- so it is off.
+CAPTURE_FIRST_STEP = os.environ.get("CB200_CAPTURE_FIRST_STEP", "0") != "0"
 _graph_cache = collections.OrderedDict()
 graph_cache_hits = 0
 _graph_warned = False
@@ -341,6 +345,25 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
             reused = None
     if reused is None and use_graph and _graph_cache:
         _graph_cache.clear()             # free the previous complex's graph pool before this batch allocates its own
+    warm_key = None
+    if use_graph and isinstance(model, torch.nn.Module):
+        from . import tensor_layers
+        warm_key = (tensor_layers.CACHE_EPOCH, sum(p._version for p in model.parameters()), sum(x._version for x in model.buffers()))
+    if (use_graph and reused is None and warm_key is not None and getattr(model, "_cb200_warm", None) == warm_key
+            and hasattr(model, "_static") and CAPTURE_FIRST_STEP):
+        # The model has run eagerly under these weights (program tables, folded weights exist): build the batch's static tables
+        # (the only host reads of a forward), capture the step BEFORE step 0 and replay all steps -- no eager forward per batch.
+        global _graph_warned
+        try:
+            model._static(batch)
+            tor_shape = (0,) if no_torsion else (topo.B * topo.R,)
+            graph, vals, z_static, graph_launches = _capture_step(batch, model, pos, topo, b, nb, tor_shape, no_torsion, scal(0)[2], device)
+        except Exception as e:
+            if not _graph_warned:
+                warnings.warn(f"cb200: CUDA-graph capture of the reverse-diffusion step failed ({type(e).__name__}: {e}); "
+                              "continuing with eager launches")
+                _graph_warned = True
+            graph, use_graph = None, False
     if reused is not None:
         global graph_cache_hits
         graph_cache_hits += 1
@@ -360,12 +383,13 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
             tor_shape = tuple(tor_score.shape)
             zs = draw(noisy, tor_shape)
             sde_step(pos, topo, tr_score, rot_score, None if no_torsion else tor_score, coeffs, zs[0], zs[1], zs[2])
+            if warm_key is not None:
+                object.__setattr__(model, "_cb200_warm", warm_key)
             if use_graph and t_idx == 0:
                 try:
                     graph, vals, z_static, graph_launches = _capture_step(batch, model, pos, topo, b, nb, tor_shape, no_torsion,
                                                                           scal(1)[2], device)
                 except Exception as e:          # capture is an optimisation: the eager loop is always correct
-                    global _graph_warned
                     if not _graph_warned:
                         warnings.warn(f"cb200: CUDA-graph capture of the reverse-diffusion step failed ({type(e).__name__}: {e}); "
                                       "continuing with eager launches")

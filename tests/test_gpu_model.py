@@ -384,6 +384,47 @@ def test_step_graph_reuse_is_bit_identical_and_follows_the_weights():
 
 
 @pytest.mark.gpu
+def test_capture_before_the_first_step_is_bit_identical():
+    """Once the model is warm, a NEW complex builds its static tables, captures the step graph before step 0 and replays all
+    steps (no eager forward): same bits as the eager-first-step path."""
+    from confidence_bootstrapping_b200 import sampling as smp
+    from confidence_bootstrapping_b200.configs import score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule
+    from confidence_bootstrapping_b200.sampling import randomize_position, sampling
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    args = score_model_args()
+    model, t2s, _ = _build(args, seed=8)
+    sched = get_t_schedule("expbeta", 5, 1, 1)
+    gs = [Batch.from_data_list([make_complex(300 + i, 50 + 15 * i, 10 + 3 * i, all_atoms=False)]) for i in range(3)]
+
+    def run_all(first_step_capture):
+        old = smp.CAPTURE_FIRST_STEP
+        smp.CAPTURE_FIRST_STEP = first_step_capture
+        smp._graph_cache.clear()
+        outs = []
+        try:
+            for i, g in enumerate(gs):
+                np.random.seed(i)
+                torch.manual_seed(i)
+                dl = [copy.deepcopy(g) for _ in range(3)]
+                randomize_position(dl, False, False, args.tr_sigma_max)
+                with injected_noise(seed=40 + i):
+                    out, _ = sampling(data_list=dl, model=model, inference_steps=5, tr_schedule=sched, rot_schedule=sched, tor_schedule=sched,
+                                      device=torch.device("cuda"), t_to_sigma=t2s, model_args=args, batch_size=3)
+                outs.append(torch.stack([d["ligand"].pos for d in out]).cpu())
+        finally:
+            smp.CAPTURE_FIRST_STEP = old
+        return outs
+
+    want = run_all(False)
+    assert getattr(model, "_cb200_warm", None) is not None
+    got = run_all(True)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
 def test_dead_output_gates_do_not_change_the_scores():
     """The per-layer receptor keep masks (score_model._dead_output_gates) only skip rows nobody reads: the scores are
     bit-identical with and without them."""
