@@ -109,8 +109,9 @@ int cb_edge_featurize(const cb_edge_feat_args* a, void* stream);
  * and sh_e (the "program"), h_e = relu(b1 + P_agg[i] + P_nbr[col[e]] + W1e (e_attr[e] + e_post[g(i)])),
  * T_s = contraction with (W2, b2).  The [E, weight_numel] tensor is never materialised.
  * Two launches: (a) accumulate -- persistent CTAs walk the (node, slot) pairs; per chunk of 16 edges the hidden
- * layer and the rank-16 update A += F^T [h;1] run as tcgen05 3xTF32 MMAs with TMEM accumulators (accum_mode 2;
- * accum_mode 1 keeps A in fp32 FFMA register tiles), the finished tile is written once to the workspace;
+ * layer and the rank-16 update A += F^T [h;1] run as tcgen05 3xTF32 MMAs with TMEM accumulators (accum_mode 2-4:
+ * lock-step, transposed, warp-specialised; accum_mode 1 keeps A in fp32 FFMA register tiles), the finished tile is
+ * written once to the workspace;
  * (b) transform + epilogue -- one CTA per 32 nodes streams the tile's accumulator rows and the W2a rows with
  * bulk copies through a shared-memory ring and finishes with mean / BatchNorm / residual.
  */
@@ -187,7 +188,10 @@ typedef struct {
      * aggregation nodes [node_begin, node_end) and needs cb_tp_conv_items(a) * n_rows * (H+4) floats            */
     float* workspace; int64_t workspace_floats;
     int32_t node_begin, node_end;
-    int32_t accum_mode;     /* accumulate kernel: 1 = fp32 FFMA register tiles, 2 = tcgen05 3xTF32 with TMEM accumulator */
+    int32_t accum_mode;     /* accumulate kernel: 1 = fp32 FFMA register tiles, 2 = tcgen05 3xTF32 with TMEM accumulator,
+                             * 3 = 2 with the accumulator transposed (D[hidden unit][f-row]; rows <= 240, H % 32 == 0),
+                             * 4 = warp-specialised transposed kernel (additionally ne == 32); 3 and 4 fall back to the
+                             * widest kernel the layer shape allows.  Results agree to fp32 rounding.              */
     int32_t flags;          /* CB_TP_RAW_SUM: write the un-normalised sums (no mean, BatchNorm, residual) */
     /* Sample-invariant contribution computed by an earlier CB_TP_RAW_SUM call: aggregation node i in
      * [pre_n0, pre_n1) additionally receives pre_sum[(i - pre_n0) % pre_period][:] before the mean and counts
