@@ -80,7 +80,7 @@ class ClockSampler:
                         self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1 if nv is not None else 0.5)
+            self._stop.wait(0.5)       # NVML queries share driver locks with the launching thread: keep them sparse
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -302,26 +302,55 @@ def run_cb200(opts):
         d2h = poses.numel() * 4 + (c.numel() * 4 if c is not None else 0)
         return dt, h2d, d2h
 
+    def confidence_leg(fbatch):
+        """crop_beyond + confidence model on the final poses (sampling.py:226-233), as a function of the poses."""
+        from confidence_bootstrapping_b200.diffusion_utils import set_time
+        from confidence_bootstrapping_b200.utils import crop_beyond
+
+        def leg(pos):
+            fbatch["ligand"].pos = pos
+            fb = crop_beyond(fbatch, conf_args.crop_beyond, True) if conf_args.crop_beyond is not None else fbatch
+            set_time(fb, 0, 0, 0, 0, fb.num_graphs, True, False, dev)
+            return conf_model(fb)[0]
+        return leg
+
     def resident_step(batch, fbatch):
-        """Inputs already in HBM: the 20-step loop + confidence scoring, timed with CUDA events."""
+        """Inputs already in HBM: the 20-step loop + confidence scoring, timed with CUDA events (one batch, one stream)."""
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         with torch.no_grad():
             pos = reverse_diffusion(batch, model, INF_STEPS, sched, sched, sched, dev, t2s, args_ns, mask_rotate)
-            if conf_model is not None:
-                from confidence_bootstrapping_b200.diffusion_utils import set_time
-                from confidence_bootstrapping_b200.utils import crop_beyond
-                fbatch["ligand"].pos = pos
-                fb = crop_beyond(fbatch, conf_args.crop_beyond, True) if conf_args.crop_beyond is not None else fbatch
-                set_time(fb, 0, 0, 0, 0, fb.num_graphs, True, False, dev)
-                conf = conf_model(fb)[0]
-            else:
-                conf = None
+            conf = confidence_leg(fbatch)(pos) if conf_model is not None else None
             if world > 1:
                 # the only collective of the path: final poses + confidences of every rank's complex
                 cbdist.gather_results([rank], [pos.view(SAMPLES, -1, 3)], [conf], world, device=dev)
         e.record()
         return s, e
+
+    def resident_pass(pairs):
+        """K steps the way sampling() runs consecutive batches: the filtering leg of batch i on the second stream while the
+        reverse-diffusion steps of batch i+1 run on the main one (sampling.FilteringLeg).  Returns (start, end, per-step end
+        events); the L2 is flushed between the steps on the main stream."""
+        from confidence_bootstrapping_b200.sampling import FilteringLeg
+        leg = FilteringLeg(dev)
+        t0, t1, marks, poses = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), [], []
+        t0.record()
+        with torch.no_grad():
+            for batch, fbatch in pairs:
+                flush.fill_(1)
+                pos = reverse_diffusion(batch, model, INF_STEPS, sched, sched, sched, dev, t2s, args_ns, mask_rotate)
+                poses.append(pos)
+                if conf_model is not None:
+                    leg.submit(confidence_leg(fbatch), pos)
+                m = torch.cuda.Event(enable_timing=True)
+                m.record()
+                marks.append(m)
+            confs = leg.finish() if conf_model is not None else [None] * len(poses)
+            if world > 1:
+                for pos, conf in zip(poses, confs):
+                    cbdist.gather_results([rank], [pos.view(SAMPLES, -1, 3)], [conf], world, device=dev)
+        t1.record()
+        return t0, t1, marks
 
     # each rank owns its own complex (weak scaling: the complex list is sharded, no data-path collective)
     base_seed = 1000 * (rank + 1)
@@ -344,16 +373,22 @@ def run_cb200(opts):
     torch.cuda.synchronize()
     launches0 = _lib.launch_count
     events = []
+    # the collector is kept out of the timed regions (a generation-2 pass over the pre-built batches showed up as single
+    # 250-380 ms steps among 165 ms ones); it runs between them instead
+    import gc
+    gc.collect()
+    gc.disable()
     with ClockSampler(local) as clocks:
         # (1) the timed region of `value`: K resident steps, nothing but the product path between the events
-        for b, fb in batches:
-            flush.fill_(1)
-            events.append(resident_step(b, fb))
+        t0, t1, marks = resident_pass(batches)
         torch.cuda.synchronize()
         launches = _lib.launch_count - launches0
-        resident_ms = [s.elapsed_time(e) for s, e in events]
+        ends = [t0] + marks[:-1] + [t1]
+        resident_ms = [a.elapsed_time(b) for a, b in zip(ends[:-1], ends[1:])]      # sums to the whole region t0 -> t1
         # (2) end to end through sampling() with host buffers
+        gc.collect()
         e2e = [e2e_step(base_seed + 900 + i) for i in range(opts.steps)]
+    gc.enable()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -386,6 +421,7 @@ def run_cb200(opts):
             "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(conf_model is not None),
             "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "ms_per_step_each": [round(float(x), 1) for x in resident_ms], "e2e_ms_each": [round(1e3 * x[0], 1) for x in e2e],
             "e2e": {"value": world * SAMPLES / e2e_s, "unit": "poses/s", "h2d_bytes_per_step": int(e2e[0][1]),
                     "d2h_bytes_per_step": int(e2e[0][2])},
         }

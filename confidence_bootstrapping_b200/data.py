@@ -182,6 +182,18 @@ def _cat0(vals, device, rep_out=None):
     return out.to(device, non_blocking=True)
 
 
+class _ReadyEvent:
+    """CUDA event recorded when a batch was collated onto the device (its H2D copies are ordered before it).  Lets a consumer
+    on ANOTHER stream wait for exactly this batch instead of for everything queued on the collate's stream.  A deep copy of
+    the batch is made of later clones, so it does not inherit the event."""
+
+    def __init__(self, ev):
+        self.ev = ev
+
+    def __deepcopy__(self, memo):
+        return _ReadyEvent(None)
+
+
 def _static_signature(batch, skip=(("ligand", "pos"),)):
     """(store, attribute, shape, dtype) of every tensor of a collated batch except the ligand pose -- no data is read.
     sampling.reverse_diffusion uses it as the cheap first key of its step-graph cache (a match is then verified element by
@@ -275,6 +287,11 @@ class Batch(HeteroData):
         b._g["_offs"] = offs
         # shape-level signature of everything but the ligand pose (sampling.reverse_diffusion: step-graph cache key)
         b._g["_static_sig"] = _static_signature(b) if device is not None else None
+        b._g["_ready"] = _ReadyEvent(None)
+        if device is not None and torch.device(device).type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(torch.device(device)))
+            b._g["_ready"] = _ReadyEvent(ev)
         return b
 
     def _rebuild_slices(self):

@@ -241,6 +241,74 @@ def _graph_pool(device):
     return _graph_pools[idx][0]
 
 
+_conf_streams = {}
+PIPELINE_CONFIDENCE = os.environ.get("CB200_PIPELINE_CONFIDENCE", "1") != "0"
+
+
+def _conf_stream(device):
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _conf_streams:
+        _conf_streams[idx] = torch.cuda.Stream(device=idx)
+    return _conf_streams[idx]
+
+
+class FilteringLeg:
+    """The confidence (filtering) leg of batch i runs on a SECOND stream while the reverse-diffusion steps of batch i+1 run
+    on the main one.  The leg has host reads (crop_beyond changes the shapes, so its static tables are rebuilt per batch);
+    on one stream they would wait for everything already enqueued -- the next batch's 20 graph replays -- and the GPU
+    would idle while the host prepares.  On its own stream the leg only waits for the event recorded after ITS batch's last
+    step, its kernels fill SMs the replays leave idle, and a host stall during the leg is hidden behind ~150 ms of queued
+    replays.  The arithmetic is unchanged (same kernels, same order within the leg).
+
+        leg = FilteringLeg(device)
+        for batch: pos = reverse_diffusion(...); leg.submit(fn, pos)     # fn(pos) -> confidence tensor; runs the PREVIOUS one
+        confidences = leg.finish()                                       # runs the last one, joins the streams
+    """
+
+    def __init__(self, device, enabled=None):
+        self.device = device
+        self.enabled = (PIPELINE_CONFIDENCE if enabled is None else enabled) and torch.device(device).type == "cuda"
+        self.pending, self.results, self._keep = None, [], []
+
+    def _run(self, fn, pos, ev):
+        if not self.enabled:
+            self.results.append(fn(pos))
+            return
+        side = _conf_stream(self.device)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            out = fn(pos)
+        pos.record_stream(side)
+        # whatever the leg read that was allocated on the main stream (the collated filtering batch in fn's closure) must not
+        # return to the allocator before the streams are joined
+        self._keep.append(fn)
+        self.results.append(out)
+
+    def submit(self, fn, pos):
+        ev = None
+        if self.enabled:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        prev, self.pending = self.pending, (fn, pos, ev)
+        if prev is not None:
+            self._run(*prev)
+
+    def finish(self):
+        if self.pending is not None:
+            self._run(*self.pending)
+            self.pending = None
+        if self.enabled:
+            main, side = torch.cuda.current_stream(self.device), _conf_stream(self.device)
+            main.wait_stream(side)
+            for r in self.results:
+                for t in (r if isinstance(r, (tuple, list)) else (r,)):
+                    if torch.is_tensor(t):
+                        t.record_stream(main)
+        out, self.results, self._keep = self.results, [], []
+        return out
+
+
 def _step_scalars(t_idx, inference_steps, tr_schedule, rot_schedule, tor_schedule, t_to_sigma, model_args, g_const, no_random, ode,
                   no_final_step_noise, temp_sampling, temp_psi, temp_sigma_data, no_torsion):
     """Host arithmetic of one reverse step (sampling.py:94-99,119-167): times, and per component the coefficients of
@@ -300,7 +368,7 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
         temp_psi = [temp_psi] * 3
     if hasattr(model_args, "crop_beyond") and model_args.crop_beyond is not None:
         raise NotImplementedError("per-step crop_beyond for the score model is not in the shipped score YAML")
-    topo = LigandTopology(batch, mask_rotate, device)
+    topo = None          # built below unless a cached step graph (which embeds it) is replayed
     pos = batch["ligand"].pos.float().contiguous()
     batch["ligand"].pos = pos
     nb = min(batch_size, N)
@@ -345,6 +413,8 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
             reused = None
     if reused is None and use_graph and _graph_cache:
         _graph_cache.clear()             # free the previous complex's graph pool before this batch allocates its own
+    if reused is None:
+        topo = LigandTopology(batch, mask_rotate, device)
     warm_key = None
     if use_graph and isinstance(model, torch.nn.Module):
         from . import tensor_layers
@@ -464,15 +534,30 @@ def _same_static(batch, mask_rotate, entry):
             return False
     except Exception:
         return False
-    flags = []
+    pairs = []
     for (key, k), ref in entry["static"].items():
         st = batch._stores.get(key)
         v = st._d.get(k) if st is not None else None
         if not torch.is_tensor(v) or v.shape != ref.shape or v.dtype != ref.dtype or v.device != ref.device:
             return False
-        flags.append(torch.equal(v, ref) if v.numel() == 0 else (v == ref).all())
-    flags = [f for f in flags if torch.is_tensor(f)]
-    return bool(torch.stack(flags).all()) if flags else True
+        if v.numel() > 0:
+            pairs.append((v, ref))
+    if not pairs:
+        return True
+    # The comparison runs on the second stream when the batch carries the event of its collate: the host then waits for that
+    # batch only, not for the previous batch's 20 replays still queued on the main stream (it can run a whole batch ahead).
+    ready = batch._g.get("_ready") if hasattr(batch, "_g") else None
+    ev = getattr(ready, "ev", None)
+    if ev is not None and pairs[0][0].is_cuda:
+        side = _conf_stream(pairs[0][0].device)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            ok = torch.stack([(v == ref).all() for v, ref in pairs]).all()
+            for v, ref in pairs:
+                v.record_stream(side)
+                ref.record_stream(side)
+            return bool(ok)
+    return bool(torch.stack([(v == ref).all() for v, ref in pairs]).all())
 
 
 def _tensor_refs(batch):
@@ -566,6 +651,8 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     g_const = {k: float(np.sqrt(np.float32(2 * np.log(getattr(model_args, f"{k}_sigma_max") / getattr(model_args, f"{k}_sigma_min")))))
                for k in ("tr", "rot", "tor")}
 
+    # (the filtering leg of a confidence model fed with the SCORE batch shares tensors with the steps: kept on one stream)
+    leg = FilteringLeg(device, enabled=None if filtering_data_list is not None else False)
     with torch.no_grad(), _inference_mode(model, confidence_model):
         for batch_id, batch in enumerate(loader):
             b = batch.num_graphs
@@ -583,19 +670,24 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                             part=1, order=2)
 
             if confidence_model is not None:
-                if filtering_data_list is not None:
-                    fb = next(filtering_loader)
-                    fb = fb.to(device)
-                    fb["ligand"].pos = pos
-                    if hasattr(filtering_model_args, "crop_beyond") and filtering_model_args.crop_beyond is not None:
-                        fb = crop_beyond(fb, filtering_model_args.crop_beyond, filtering_model_args.all_atoms)
-                    set_time(fb, 0, 0, 0, 0, b, filtering_model_args.all_atoms, asyncronous_noise_schedule, device)
-                    out = confidence_model(fb)
-                else:
-                    out = confidence_model(batch)
-                if type(out) is tuple:
-                    out = out[0]
-                confidence.append(out)
+                fb0 = next(filtering_loader) if filtering_data_list is not None else None
+
+                def conf_leg(p, fb=fb0, batch=batch, b=b):
+                    if fb is not None:
+                        fb = fb.to(device)           # (already there when the loader collates onto the device)
+                        fb["ligand"].pos = p
+                        if hasattr(filtering_model_args, "crop_beyond") and filtering_model_args.crop_beyond is not None:
+                            fb = crop_beyond(fb, filtering_model_args.crop_beyond, filtering_model_args.all_atoms)
+                        set_time(fb, 0, 0, 0, 0, b, filtering_model_args.all_atoms, asyncronous_noise_schedule, device)
+                        out = confidence_model(fb)
+                    else:
+                        out = confidence_model(batch)
+                    return out[0] if type(out) is tuple else out
+
+                leg.submit(conf_leg, pos)        # runs the previous batch's leg while this batch's steps are in flight
+        done = leg.finish()
+        if confidence_model is not None:
+            confidence = done
 
     if confidence_model is not None:
         confidence = torch.cat(confidence, dim=0)

@@ -31,6 +31,26 @@ ACCUM_MODE = int(os.environ.get("CB200_ACCUM_MODE", "4"))
 CACHE_EPOCH = 0
 
 
+_WORKSPACES = {}    # device -> grow-only K3 workspace of the eager launches
+
+
+def _workspace(n_floats, dev):
+    """Accumulator workspace of one K3 call.  Eager launches share ONE grow-only buffer per device: consecutive calls on a
+    stream use it one after the other, and the multi-GB cudaMalloc / cudaFree a differently sized request can trigger in the
+    caching allocator (the confidence leg's shapes change with every crop_beyond: single 250-380 ms steps among 165 ms ones)
+    disappears.  While a CUDA graph is being captured the buffer comes from the graph's memory pool instead, so that the
+    graph owns what it points to."""
+    if DEBUG_KEEP_WORKSPACE is not None or torch.cuda.is_current_stream_capturing():
+        return torch.empty(n_floats, dtype=torch.float32, device=dev)
+    key = (torch.device(dev).index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < n_floats:
+        grow = n_floats if buf is None else max(n_floats, min(int(buf.numel() * 1.5), WORKSPACE_BYTES // 4))
+        _WORKSPACES[key] = buf = None          # release the old block to the allocator before asking for the larger one
+        _WORKSPACES[key] = buf = torch.empty(grow, dtype=torch.float32, device=dev)
+    return buf[:n_floats]
+
+
 def _bump_epoch():
     global CACHE_EPOCH
     CACHE_EPOCH += 1
@@ -432,7 +452,7 @@ class TensorProductConvLayer(nn.Module):
         for c0 in range(0, n_out, step):
             a.node_begin, a.node_end = c0, min(n_out, c0 + step)
             it = _lib.tp_conv_items(a)
-            ws = torch.empty(max(it, 1) * per_item, dtype=torch.float32, device=dev)
+            ws = _workspace(max(it, 1) * per_item, dev)
             a.workspace, a.workspace_floats = ws.data_ptr(), ws.numel()
             _lib.tp_conv_forward(a)
             if DEBUG_KEEP_WORKSPACE is not None:

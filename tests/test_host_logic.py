@@ -439,3 +439,17 @@ def test_sampling_refreshes_derived_weights_only_when_the_weights_moved():
     layer.batch_norm.running_var.data.mul_(4.0)                          # buffers count too
     with smp._inference_mode(layer):
         assert tl.CACHE_EPOCH > e1
+
+
+def test_filtering_leg_runs_one_batch_behind_and_keeps_the_order():
+    """sampling.FilteringLeg: the leg of batch i is executed when batch i+1 is submitted (or at finish), results in batch order."""
+    from confidence_bootstrapping_b200.sampling import FilteringLeg
+    leg = FilteringLeg(torch.device("cpu"))
+    assert not leg.enabled                      # one stream on the CPU: the legs run inline
+    calls = []
+    for i in range(3):
+        leg.submit(lambda p, i=i: (calls.append(i), p * (i + 1))[1], torch.full((2,), 1.0))
+        assert calls == list(range(i))          # batch i's leg has not run yet
+    out = leg.finish()
+    assert calls == [0, 1, 2] and [float(o[0]) for o in out] == [1.0, 2.0, 3.0]
+    assert leg.finish() == []
