@@ -670,7 +670,12 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                             part=1, order=2)
 
             if confidence_model is not None:
-                fb0 = next(filtering_loader) if filtering_data_list is not None else None
+                # the filtering batch is collated (host compare + H2D, ~7 ms) on the leg's stream AFTER this batch's steps
+                # were enqueued: on the main stream its copies would queue behind the 20 replays and block the host
+                fb0 = None
+                if filtering_data_list is not None:
+                    with (torch.cuda.stream(_conf_stream(device)) if leg.enabled else contextlib.nullcontext()):
+                        fb0 = next(filtering_loader)
 
                 def conf_leg(p, fb=fb0, batch=batch, b=b):
                     if fb is not None:
