@@ -179,15 +179,21 @@ def _inference_mode(*models):
 
 
 def _weights_signature(model):
-    """(data pointers, [L2 norms | L1 norms] of every parameter and floating buffer) -- two multi-tensor launches and one
-    small D2H per sampling call."""
+    """(data pointers, 3 float64 checksums of ALL parameters and floating buffers): the flattened weights projected on two fixed
+    pseudo-random vectors (sensitive to any element changing, sign flips and permutations included) and their L1 norm --
+    two concatenation launches, a few reductions and one small D2H per sampling call."""
     ts = [p.detach() for p in model.parameters()] + [b.detach() for b in model.buffers() if b.is_floating_point()]
     ts = [t for t in ts if t.numel() > 0]
     if not ts:
         return (), torch.zeros(0, dtype=torch.float64)
     ptrs = tuple(t.data_ptr() for t in ts)
-    fl = [t.float() if t.dtype != torch.float32 else t for t in ts]
-    sig = torch.stack(list(torch._foreach_norm(fl, 2)) + list(torch._foreach_norm(fl, 1))).double().cpu()
+    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in ts]).double()
+    proj = getattr(model, "_cb200_sig_proj", None)
+    if proj is None or proj.shape[1] != flat.numel() or proj.device != flat.device:
+        g = torch.Generator(device="cpu").manual_seed(0x5EED)
+        proj = torch.rand((2, flat.numel()), generator=g, dtype=torch.float64).add_(0.5).to(flat.device)
+        object.__setattr__(model, "_cb200_sig_proj", proj)
+    sig = torch.cat([proj @ flat, flat.abs().sum().reshape(1)]).cpu()
     return ptrs, sig
 
 
