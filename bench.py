@@ -150,7 +150,7 @@ def run_reference(opts):
     from confidence_bootstrapping_b200.utils import get_model
     from confidence_bootstrapping_b200.diffusion_utils import t_to_sigma
     from oracle import model as om, sampler as osamp
-    cores = os.cpu_count() or 1
+    cores = opts.ref_threads or os.cpu_count() or 1       # threads actually used (--ref-threads 1: the single-thread figure)
     torch.set_num_threads(cores)
     args_ns, conf_args = score_model_args(), confidence_model_args()
     torch.manual_seed(0)
@@ -537,6 +537,7 @@ def main():
     ap.add_argument("--no-confidence", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-samples", type=int, default=0, help="poses per reference step (0 = sized to the run: 8/4/2/1)")
+    ap.add_argument("--ref-threads", type=int, default=0, help="host threads of the reference arm (0 = all cores)")
     ap.add_argument("--no-config3", action="store_true", help="skip the strong-scaling pass over the 64-complex list")
     opts = ap.parse_args()
     if opts.impl == "reference":
