@@ -195,6 +195,8 @@ def workload_config(confidence):
                         f"{INF_STEPS} reverse-diffusion steps" + (" + confidence scoring" if confidence else " (score model)"),
             "n_residues": N_RES, "n_ligand_atoms": N_LIG, "samples": SAMPLES, "inference_steps": INF_STEPS,
             "confidence_scoring": bool(confidence), "l2": "flushed between timed steps (256 MiB write)",
+            "timed_region": "K consecutive steps as sampling() runs consecutive batches: the filtering leg of step i on a second "
+                            "stream while the reverse-diffusion steps of step i+1 run; ms_per_step = whole region / K",
             "weights": "seeded random init (checkpoints unavailable offline)"}
 
 
