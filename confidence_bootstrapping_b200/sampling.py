@@ -205,10 +205,10 @@ USE_CUDA_GRAPH = os.environ.get("CB200_CUDA_GRAPH", "1") != "0"
 # pool (the K3 workspaces: up to 16 GiB per layer for 1000-residue complexes) is free for the new capture.  (Two cached graphs
 # drove a mixed-size run -- BASELINE configs[3], N_r up to 1000 -- out of memory: 49 GiB in graph pools + fragmentation.)
 GRAPH_CACHE_SIZE = int(os.environ.get("CB200_GRAPH_CACHE", "1"))
-# Option: once a model has run one eager step under its current weights, later batches capture their step graph BEFORE step 0
-# (static tables built by model._static, no eager forward per batch).  Bit-identical (tests) but measured no faster -- the
-# eager step it saves overlapped the capture's host time anyway (configs[3]: 86 vs 91 poses/s, within noise) -- so it is off.
-CAPTURE_FIRST_STEP = os.environ.get("CB200_CAPTURE_FIRST_STEP", "0") != "0"
+# Once a model has run one eager step under its current weights, later batches capture their step graph BEFORE step 0 (static
+# tables built by model._static, no eager forward per batch).  Bit-identical (tests); in-process A/B of end-to-end calls on
+# new complexes: 194.2 -> 189.5 ms (profiles/ab_e2e.py).
+CAPTURE_FIRST_STEP = os.environ.get("CB200_CAPTURE_FIRST_STEP", "1") != "0"
 _graph_cache = collections.OrderedDict()
 graph_cache_hits = 0
 _graph_warned = False
