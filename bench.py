@@ -64,7 +64,11 @@ class ClockSampler:
 
     def _run(self):
         nv, h = self._nvml()
+        period = float(os.environ.get("CB200_CLOCK_SAMPLE_PERIOD", "0.5"))
         while not self._stop.is_set():
+            if period <= 0:          # experiment: no sampling at all
+                self._stop.wait(0.5)
+                continue
             try:
                 if nv is not None:
                     sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
@@ -80,7 +84,7 @@ class ClockSampler:
                         self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.5)       # NVML queries share driver locks with the launching thread: keep them sparse
+            self._stop.wait(period)    # NVML queries share driver locks with the launching thread: keep them sparse
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -370,27 +374,37 @@ def run_cb200(opts):
     batches = fresh_batches(opts.steps)
     for b in batches[:1]:
         resident_step(copy.deepcopy(b[0]), copy.deepcopy(b[1]))       # warm the resident path too
+    # ... and its two-stream form: the filtering leg's buffers live in the second stream's allocator pool (first use: 15 GB)
+    resident_pass(fresh_batches(2))
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = _lib.launch_count
     events = []
-    # the collector is kept out of the timed regions (a generation-2 pass over the pre-built batches showed up as single
-    # 250-380 ms steps among 165 ms ones); it runs between them instead
+    # The pre-built batches and models are moved to the collector's permanent generation: the collector stays ON (reference
+    # cycles that hold device tensors must keep being freed, or the allocator has to cudaMalloc new multi-GB blocks), but its
+    # passes inside the timed regions only walk the objects created there.
     import gc
     gc.collect()
-    gc.disable()
+    gc.freeze()
     with ClockSampler(local) as clocks:
         # (1) the timed region of `value`: K resident steps, nothing but the product path between the events
+        ms0 = torch.cuda.memory_stats()
         t0, t1, marks = resident_pass(batches)
         torch.cuda.synchronize()
+        ms1 = torch.cuda.memory_stats()
+        alloc_diag = {"reserved_GiB": round(ms1["reserved_bytes.all.current"] / 2 ** 30, 1),
+                      "new_segments_in_timed_region": int(ms1["segment.all.allocated"] - ms0["segment.all.allocated"]),
+                      "freed_segments_in_timed_region": int(ms1["segment.all.freed"] - ms0["segment.all.freed"]),
+                      "alloc_retries": int(ms1["num_alloc_retries"] - ms0["num_alloc_retries"])}
         launches = _lib.launch_count - launches0
         ends = [t0] + marks[:-1] + [t1]
         resident_ms = [a.elapsed_time(b) for a, b in zip(ends[:-1], ends[1:])]      # sums to the whole region t0 -> t1
         # (2) end to end through sampling() with host buffers
         gc.collect()
         e2e = [e2e_step(base_seed + 900 + i) for i in range(opts.steps)]
-    gc.enable()
+    gc.unfreeze()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -423,7 +437,7 @@ def run_cb200(opts):
             "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(conf_model is not None),
             "clocks": clocks.summary(), "gpu_launches": int(launches),
-            "ms_per_step_each": [round(float(x), 1) for x in resident_ms], "e2e_ms_each": [round(1e3 * x[0], 1) for x in e2e],
+            "allocator": alloc_diag, "ms_per_step_each": [round(float(x), 1) for x in resident_ms], "e2e_ms_each": [round(1e3 * x[0], 1) for x in e2e],
             "e2e": {"value": world * SAMPLES / e2e_s, "unit": "poses/s", "h2d_bytes_per_step": int(e2e[0][1]),
                     "d2h_bytes_per_step": int(e2e[0][2])},
         }

@@ -1,0 +1,9 @@
+mkdir -p gpurun_out/r2
+for P in 0 0.5; do
+CB200_CLOCK_SAMPLE_PERIOD=$P timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --no-config3 > gpurun_out/r2/bench_s20_p$P.json 2> gpurun_out/r2/bench_s20_p$P.err
+python - <<PY
+import json
+j=json.loads(open('gpurun_out/r2/bench_s20_p$P.json').read().strip().splitlines()[-1])
+print('period $P', round(j['value'],1), round(j['e2e']['value'],1)); print(j['ms_per_step_each']); print(j['e2e_ms_each'])
+PY
+done
