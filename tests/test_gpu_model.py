@@ -425,6 +425,54 @@ def test_capture_before_the_first_step_is_bit_identical():
 
 
 @pytest.mark.gpu
+def test_multi_batch_sampling_with_two_streams_equals_the_single_stream_path():
+    """sampling() over several batches of one complex (samples_per_complex > batch_size, what inference.py does) with the
+    confidence model: batches 2.. replay the cached step graph and every filtering leg runs one batch behind on the second
+    stream.  Poses and confidences must be bit-identical to the plain path (no graph cache, one stream)."""
+    from confidence_bootstrapping_b200 import sampling as smp
+    from confidence_bootstrapping_b200.configs import confidence_model_args, score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule, t_to_sigma as t2s_full
+    from confidence_bootstrapping_b200.sampling import randomize_position, sampling
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    from confidence_bootstrapping_b200.utils import get_model
+    dev = torch.device("cuda")
+    args, cargs = score_model_args(), confidence_model_args()
+    t2s = partial(t2s_full, args=args)
+    torch.manual_seed(0)
+    model = get_model(args, dev, t_to_sigma=t2s, no_parallel=True).eval()
+    torch.manual_seed(1)
+    cmodel = get_model(cargs, dev, t_to_sigma=None, no_parallel=True, confidence_mode=True).eval()
+    g = Batch.from_data_list([make_complex(431, 90, 14, all_atoms=True)])
+    sched = get_t_schedule("expbeta", 5, 1, 1)
+
+    def run(pipelined):
+        np.random.seed(7)
+        torch.manual_seed(7)
+        dl = [copy.deepcopy(g) for _ in range(9)]
+        randomize_position(dl, False, False, args.tr_sigma_max)
+        fl = copy.deepcopy(dl)
+        saved = (smp.PIPELINE_CONFIDENCE, smp.GRAPH_CACHE_SIZE)
+        smp.PIPELINE_CONFIDENCE, smp.GRAPH_CACHE_SIZE = (True, 1) if pipelined else (False, 0)
+        smp._graph_cache.clear()
+        h0 = smp.graph_cache_hits
+        try:
+            with injected_noise(seed=77):
+                out, conf = sampling(data_list=dl, model=model, inference_steps=5, tr_schedule=sched, rot_schedule=sched, tor_schedule=sched,
+                                     device=dev, t_to_sigma=t2s, model_args=args, batch_size=3, confidence_model=cmodel,
+                                     filtering_data_list=fl, filtering_model_args=cargs)
+        finally:
+            smp.PIPELINE_CONFIDENCE, smp.GRAPH_CACHE_SIZE = saved
+        return torch.stack([d["ligand"].pos for d in out]).cpu(), conf.cpu(), smp.graph_cache_hits - h0
+
+    pos0, conf0, hits0 = run(False)
+    pos1, conf1, hits1 = run(True)
+    assert hits0 == 0 and hits1 == 2                    # 3 batches: capture, then two replays of the cached graph
+    assert conf1.shape == (9,) and torch.equal(pos0, pos1) and torch.equal(conf0, conf1)
+    smp._graph_cache.clear()
+
+
+@pytest.mark.gpu
 def test_dead_output_gates_do_not_change_the_scores():
     """The per-layer receptor keep masks (score_model._dead_output_gates) only skip rows nobody reads: the scores are
     bit-identical with and without them."""
