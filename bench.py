@@ -487,7 +487,7 @@ def config3_pass(rank, world, dev, model, conf_model, args_ns, conf_args, t2s, s
     import torch.distributed as dist
     from confidence_bootstrapping_b200 import dist as cbdist
     from confidence_bootstrapping_b200.data import Batch
-    from confidence_bootstrapping_b200.sampling import randomize_position, sampling
+    from confidence_bootstrapping_b200.sampling import randomize_position, sampling_many
     from confidence_bootstrapping_b200.synthetic import make_complex
     sizes = config3_sizes(n_complexes)
     costs = [cbdist.estimate_cost(nl, nr, samples) for nr, nl in sizes]
@@ -507,8 +507,9 @@ def config3_pass(rank, world, dev, model, conf_model, args_ns, conf_args, t2s, s
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     poses, confs = [], []
-    for i, dl, fl in work:
-        out, conf = sampling(data_list=dl, filtering_data_list=fl, **kw)
+    # the callers' `for complex: sampling(...)` loop as one pipelined call (sampling.sampling_many): same results, the filtering
+    # leg of complex i overlaps the collate / capture / steps of complex i+1
+    for out, conf in sampling_many([(dl, fl) for _, dl, fl in work], **kw):
         poses.append(torch.stack([d["ligand"].pos for d in out]))
         confs.append(conf)
     torch.cuda.synchronize()

@@ -288,7 +288,9 @@ class FilteringLeg:
         pos.record_stream(side)
         # whatever the leg read that was allocated on the main stream (the collated filtering batch in fn's closure) must not
         # return to the allocator before the streams are joined
+        # (a leg's host reads complete only after every earlier leg on the stream has: two entries are enough)
         self._keep.append(fn)
+        del self._keep[:-2]
         self.results.append(out)
 
     def submit(self, fn, pos):
@@ -623,6 +625,85 @@ def _capture_step(batch, model, pos, topo, b, nb, tor_shape, no_torsion, noisy, 
     return graph, vals, z_static, _lib.launch_count - l0
 
 
+_SAMPLING_DEFAULTS = dict(no_random=False, ode=False, visualization_list=None, confidence_model=None, filtering_data_list=None,
+                          filtering_model_args=None, asyncronous_noise_schedule=False, t_schedule=None, batch_size=32,
+                          no_final_step_noise=False, pivot=None, return_full_trajectory=False, temp_sampling=1.0, temp_psi=0.0,
+                          temp_sigma_data=0.5, return_features=False)
+
+
+def _sample_batches(leg, data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,
+                    no_random, ode, visualization_list, confidence_model, filtering_data_list, filtering_model_args,
+                    asyncronous_noise_schedule, t_schedule, batch_size, no_final_step_noise, temp_sampling, temp_psi,
+                    temp_sigma_data):
+    """The batch loop of one sampling() call (sampling.py:78-262): reverse diffusion per batch on the current stream, the
+    filtering leg of every batch handed to `leg` (which runs it one submission later).  Returns the number of legs submitted."""
+    N = len(data_list)
+    # batches are collated straight onto the device: attributes shared by the N copies of a complex cross the bus once
+    loader = DataLoader(data_list, batch_size=batch_size, device=device)
+    mask_rotate = _mask_rotate_of(data_list[0])
+    filtering_loader = None
+    if confidence_model is not None and filtering_data_list is not None:
+        filtering_loader = iter(DataLoader(filtering_data_list, batch_size=batch_size, device=device))
+    if not _is_iterable(temp_sampling):
+        temp_sampling = [temp_sampling] * 3
+    if not _is_iterable(temp_psi):
+        temp_psi = [temp_psi] * 3
+    assert len(temp_sampling) == 3 and len(temp_psi) == 3
+    n_legs = 0
+    for batch_id, batch in enumerate(loader):
+        b = batch.num_graphs
+        batch = batch.to(device)
+        pos = reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device,
+                                t_to_sigma, model_args, mask_rotate, noise_rows=min(batch_size, N), no_random=no_random,
+                                ode=ode, t_schedule=t_schedule, no_final_step_noise=no_final_step_noise,
+                                temp_sampling=temp_sampling, temp_psi=temp_psi, temp_sigma_data=temp_sigma_data)
+        n = pos.shape[0] // b
+        for i in range(b):
+            data_list[batch_id * batch_size + i]["ligand"].pos = pos[i * n:n * (i + 1)]
+        if visualization_list is not None:
+            for idx, vis in enumerate(visualization_list):
+                vis.add((data_list[idx]["ligand"].pos.detach().cpu() + data_list[idx].original_center.detach().cpu()),
+                        part=1, order=2)
+
+        if confidence_model is not None:
+            # the filtering batch is collated (host compare + H2D, ~7 ms) on the leg's stream AFTER this batch's steps
+            # were enqueued: on the main stream its copies would queue behind the 20 replays and block the host
+            fb0 = None
+            if filtering_loader is not None:
+                with (torch.cuda.stream(_conf_stream(device)) if leg.enabled else contextlib.nullcontext()):
+                    fb0 = next(filtering_loader)
+
+            def conf_leg(p, fb=fb0, batch=batch, b=b):
+                if fb is not None:
+                    fb = fb.to(device)           # (already there when the loader collates onto the device)
+                    fb["ligand"].pos = p
+                    if hasattr(filtering_model_args, "crop_beyond") and filtering_model_args.crop_beyond is not None:
+                        fb = crop_beyond(fb, filtering_model_args.crop_beyond, filtering_model_args.all_atoms)
+                    set_time(fb, 0, 0, 0, 0, b, filtering_model_args.all_atoms, asyncronous_noise_schedule, device)
+                    out = confidence_model(fb)
+                else:
+                    out = confidence_model(batch)
+                return out[0] if type(out) is tuple else out
+
+            leg.submit(conf_leg, pos)        # runs the previous leg while this batch's steps are in flight
+            n_legs += 1
+    return n_legs
+
+
+def _check_sampling_flags(N, batch_size, return_features, return_full_trajectory, pivot, asyncronous_noise_schedule, svgd0, svgd1):
+    if return_features:
+        assert batch_size >= N, "Not implemented yet"
+    if svgd0 is not None and svgd1 is not None:
+        raise NotImplementedError("SVGD coupling (sampling.py:169-218) is an optional branch outside the hot path")
+    assert not (return_full_trajectory or return_features or pivot), "Not implemented yet in new inference version"
+    assert not asyncronous_noise_schedule
+
+
+def _finish_confidence(chunks):
+    confidence = torch.cat(chunks, dim=0)
+    return torch.nan_to_num(confidence, nan=-1000)
+
+
 def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,
              no_random=False, ode=False, visualization_list=None, confidence_model=None, filtering_data_list=None,
              filtering_model_args=None, asyncronous_noise_schedule=False, t_schedule=None, batch_size=32,
@@ -632,75 +713,55 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
              svgd_repulsive_weight_log_1=None, svgd_kernel_size_log_0=None, svgd_kernel_size_log_1=None,
              svgd_langevin_weight_log_0=None, svgd_langevin_weight_log_1=None, svgd_rot_log_rel_weight=0.0,
              svgd_tor_log_rel_weight=0.0, svgd_use_x0=False):
-    N = len(data_list)
-    if return_features:
-        assert batch_size >= N, "Not implemented yet"
-    if svgd_weight_log_0 is not None and svgd_weight_log_1 is not None:
-        raise NotImplementedError("SVGD coupling (sampling.py:169-218) is an optional branch outside the hot path")
-    assert not (return_full_trajectory or return_features or pivot), "Not implemented yet in new inference version"
-    assert not asyncronous_noise_schedule
-
-    # batches are collated straight onto the device: attributes shared by the N copies of a complex cross the bus once
-    loader = DataLoader(data_list, batch_size=batch_size, device=device)
-    mask_rotate = _mask_rotate_of(data_list[0])
-    confidence = None
-    if confidence_model is not None:
-        filtering_loader = iter(DataLoader(filtering_data_list, batch_size=batch_size, device=device)) if filtering_data_list is not None else None
-        confidence = []
-    if not _is_iterable(temp_sampling):
-        temp_sampling = [temp_sampling] * 3
-    if not _is_iterable(temp_psi):
-        temp_psi = [temp_psi] * 3
-    assert len(temp_sampling) == 3 and len(temp_psi) == 3
-    no_torsion = bool(model_args.no_torsion)
-    all_atoms = "all_atoms" in model_args and model_args.all_atoms
-    g_const = {k: float(np.sqrt(np.float32(2 * np.log(getattr(model_args, f"{k}_sigma_max") / getattr(model_args, f"{k}_sigma_min")))))
-               for k in ("tr", "rot", "tor")}
-
+    """utils/sampling.py:59 `sampling()`: same signature, same return value `(data_list, confidence)`."""
+    _check_sampling_flags(len(data_list), batch_size, return_features, return_full_trajectory, pivot, asyncronous_noise_schedule,
+                          svgd_weight_log_0, svgd_weight_log_1)
     # (the filtering leg of a confidence model fed with the SCORE batch shares tensors with the steps: kept on one stream)
     leg = FilteringLeg(device, enabled=None if filtering_data_list is not None else False)
     with torch.no_grad(), _inference_mode(model, confidence_model):
-        for batch_id, batch in enumerate(loader):
-            b = batch.num_graphs
-            batch = batch.to(device)
-            pos = reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device,
-                                    t_to_sigma, model_args, mask_rotate, noise_rows=min(batch_size, N), no_random=no_random,
-                                    ode=ode, t_schedule=t_schedule, no_final_step_noise=no_final_step_noise,
-                                    temp_sampling=temp_sampling, temp_psi=temp_psi, temp_sigma_data=temp_sigma_data)
-            n = pos.shape[0] // b
-            for i in range(b):
-                data_list[batch_id * batch_size + i]["ligand"].pos = pos[i * n:n * (i + 1)]
-            if visualization_list is not None:
-                for idx, vis in enumerate(visualization_list):
-                    vis.add((data_list[idx]["ligand"].pos.detach().cpu() + data_list[idx].original_center.detach().cpu()),
-                            part=1, order=2)
-
-            if confidence_model is not None:
-                # the filtering batch is collated (host compare + H2D, ~7 ms) on the leg's stream AFTER this batch's steps
-                # were enqueued: on the main stream its copies would queue behind the 20 replays and block the host
-                fb0 = None
-                if filtering_data_list is not None:
-                    with (torch.cuda.stream(_conf_stream(device)) if leg.enabled else contextlib.nullcontext()):
-                        fb0 = next(filtering_loader)
-
-                def conf_leg(p, fb=fb0, batch=batch, b=b):
-                    if fb is not None:
-                        fb = fb.to(device)           # (already there when the loader collates onto the device)
-                        fb["ligand"].pos = p
-                        if hasattr(filtering_model_args, "crop_beyond") and filtering_model_args.crop_beyond is not None:
-                            fb = crop_beyond(fb, filtering_model_args.crop_beyond, filtering_model_args.all_atoms)
-                        set_time(fb, 0, 0, 0, 0, b, filtering_model_args.all_atoms, asyncronous_noise_schedule, device)
-                        out = confidence_model(fb)
-                    else:
-                        out = confidence_model(batch)
-                    return out[0] if type(out) is tuple else out
-
-                leg.submit(conf_leg, pos)        # runs the previous batch's leg while this batch's steps are in flight
+        _sample_batches(leg, data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args,
+                        no_random, ode, visualization_list, confidence_model, filtering_data_list, filtering_model_args,
+                        asyncronous_noise_schedule, t_schedule, batch_size, no_final_step_noise, temp_sampling, temp_psi,
+                        temp_sigma_data)
         done = leg.finish()
-        if confidence_model is not None:
-            confidence = done
-
-    if confidence_model is not None:
-        confidence = torch.cat(confidence, dim=0)
-        confidence = torch.nan_to_num(confidence, nan=-1000)
+    confidence = _finish_confidence(done) if confidence_model is not None else None
     return data_list, confidence
+
+
+def sampling_many(requests, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma, model_args, **kwargs):
+    """The callers' loop `for complex in loader: sampling(data_list, ...)` (inference.py:432-470, finetune_train.py:168-195,
+    bootstrapping.py:106-140) as ONE call: `requests` is a sequence of `(data_list, filtering_data_list)` pairs (or bare
+    data_lists), the other arguments are sampling()'s and apply to every request.  Returns `[(data_list, confidence), ...]`
+    with exactly the values the separate calls return -- but the filtering leg of complex i runs on the second stream while
+    complex i+1 is collated, captured and stepped on the main one, so neither the host work of a new complex (collate,
+    static tables, graph capture: ~40 ms) nor the shape-dependent host reads of the leg leave the GPU idle."""
+    kw = dict(_SAMPLING_DEFAULTS)
+    unknown = set(kwargs) - set(kw) - {"filtering_data_list"}
+    svgd = {k: kwargs.pop(k) for k in list(kwargs) if k.startswith("svgd_")}
+    unknown = {k for k in unknown if not k.startswith("svgd_")}
+    if unknown:
+        raise TypeError(f"sampling_many() got unexpected keyword arguments {sorted(unknown)}")
+    kw.update(kwargs)
+    kw.pop("filtering_data_list")
+    confidence_model = kw["confidence_model"]
+    reqs = [(r, None) if not (isinstance(r, (tuple, list)) and len(r) == 2 and (r[1] is None or isinstance(r[1], (list, tuple)))
+                              and isinstance(r[0], (list, tuple))) else tuple(r) for r in requests]
+    for dl, _ in reqs:
+        _check_sampling_flags(len(dl), kw["batch_size"], kw["return_features"], kw["return_full_trajectory"], kw["pivot"],
+                              kw["asyncronous_noise_schedule"], svgd.get("svgd_weight_log_0"), svgd.get("svgd_weight_log_1"))
+    pipelined = confidence_model is not None and all(fl is not None for _, fl in reqs)
+    leg = FilteringLeg(device, enabled=None if pipelined else False)
+    counts = []
+    with torch.no_grad(), _inference_mode(model, confidence_model):
+        for dl, fl in reqs:
+            counts.append(_sample_batches(leg, dl, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma,
+                                          model_args, kw["no_random"], kw["ode"], kw["visualization_list"], confidence_model, fl,
+                                          kw["filtering_model_args"], kw["asyncronous_noise_schedule"], kw["t_schedule"],
+                                          kw["batch_size"], kw["no_final_step_noise"], kw["temp_sampling"], kw["temp_psi"],
+                                          kw["temp_sigma_data"]))
+        done = leg.finish()
+    out, k = [], 0
+    for (dl, _), c in zip(reqs, counts):
+        out.append((dl, _finish_confidence(done[k:k + c]) if confidence_model is not None else None))
+        k += c
+    return out

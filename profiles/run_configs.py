@@ -27,7 +27,7 @@ from confidence_bootstrapping_b200 import dist as cbdist  # noqa: E402
 from confidence_bootstrapping_b200.configs import all_atom_score_model_args, confidence_model_args, score_model_args  # noqa: E402
 from confidence_bootstrapping_b200.data import Batch  # noqa: E402
 from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule, t_to_sigma  # noqa: E402
-from confidence_bootstrapping_b200.sampling import randomize_position, sampling  # noqa: E402
+from confidence_bootstrapping_b200.sampling import randomize_position, sampling, sampling_many  # noqa: E402
 from confidence_bootstrapping_b200.synthetic import make_complex  # noqa: E402
 from confidence_bootstrapping_b200.utils import get_model  # noqa: E402
 
@@ -93,10 +93,9 @@ def main():
 
     def run():
         poses, confs = [], []
-        for i, dl, fl in work:
-            if not dl:
-                continue
-            out, conf = sampling(data_list=dl, filtering_data_list=fl, **kw)
+        todo = [(dl, fl) for i, dl, fl in work if dl]
+        # one pipelined call for the rank's complexes (sampling.sampling_many == the loop of sampling() calls, same results)
+        for out, conf in sampling_many(todo, **kw):
             poses.append(torch.stack([d["ligand"].pos for d in out]))
             confs.append(conf)
         return poses, confs

@@ -473,6 +473,59 @@ def test_multi_batch_sampling_with_two_streams_equals_the_single_stream_path():
 
 
 @pytest.mark.gpu
+def test_sampling_many_equals_the_loop_of_sampling_calls():
+    """sampling_many (the callers' per-complex loop as one pipelined call: filtering leg of complex i on the second stream
+    while complex i+1 is collated / captured / stepped) returns exactly what separate sampling() calls return."""
+    from confidence_bootstrapping_b200 import sampling as smp
+    from confidence_bootstrapping_b200.configs import confidence_model_args, score_model_args
+    from confidence_bootstrapping_b200.data import Batch
+    from confidence_bootstrapping_b200.diffusion_utils import get_t_schedule, t_to_sigma as t2s_full
+    from confidence_bootstrapping_b200.sampling import randomize_position, sampling, sampling_many
+    from confidence_bootstrapping_b200.synthetic import make_complex
+    from confidence_bootstrapping_b200.utils import get_model
+    dev = torch.device("cuda")
+    args, cargs = score_model_args(), confidence_model_args()
+    t2s = partial(t2s_full, args=args)
+    torch.manual_seed(0)
+    model = get_model(args, dev, t_to_sigma=t2s, no_parallel=True).eval()
+    torch.manual_seed(1)
+    cmodel = get_model(cargs, dev, t_to_sigma=None, no_parallel=True, confidence_mode=True).eval()
+    sizes = [(120, 12), (60, 9), (200, 20), (60, 9)]
+    graphs = [Batch.from_data_list([make_complex(520 + i, nr, nl, all_atoms=True)]) for i, (nr, nl) in enumerate(sizes)]
+    sched = get_t_schedule("expbeta", 5, 1, 1)
+    kw = dict(model=model, inference_steps=5, tr_schedule=sched, rot_schedule=sched, tor_schedule=sched, device=dev, t_to_sigma=t2s,
+              model_args=args, batch_size=4, confidence_model=cmodel, filtering_model_args=cargs)
+
+    def inputs():
+        reqs = []
+        for i, g in enumerate(graphs):
+            np.random.seed(i)
+            torch.manual_seed(i)
+            dl = [copy.deepcopy(g) for _ in range(4 if i != 2 else 8)]       # complex 2: two batches
+            randomize_position(dl, False, False, args.tr_sigma_max)
+            reqs.append((dl, copy.deepcopy(dl)))
+        return reqs
+
+    smp._graph_cache.clear()
+    with injected_noise(seed=21):
+        want = [sampling(data_list=dl, filtering_data_list=fl, **kw) for dl, fl in inputs()]
+    smp._graph_cache.clear()
+    with injected_noise(seed=21):
+        got = sampling_many(inputs(), **kw)
+    assert len(got) == len(want)
+    for (o1, c1), (o0, c0) in zip(got, want):
+        assert torch.equal(torch.stack([d["ligand"].pos for d in o1]), torch.stack([d["ligand"].pos for d in o0]))
+        assert torch.equal(c1, c0)
+    # bare data lists (no confidence model) work too, and unknown keywords are refused
+    with injected_noise(seed=22):
+        plain = sampling_many([dl for dl, _ in inputs()], **{**kw, "confidence_model": None})
+    assert all(c is None for _, c in plain)
+    with pytest.raises(TypeError):
+        sampling_many(inputs(), **kw, no_such_flag=1)
+    smp._graph_cache.clear()
+
+
+@pytest.mark.gpu
 def test_dead_output_gates_do_not_change_the_scores():
     """The per-layer receptor keep masks (score_model._dead_output_gates) only skip rows nobody reads: the scores are
     bit-identical with and without them."""
