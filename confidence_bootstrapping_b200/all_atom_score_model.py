@@ -15,7 +15,7 @@ from types import SimpleNamespace
 import torch
 from torch import nn
 
-from .graph import EdgeEmbedder, radius_edges, radius_edges_transposed, static_edges
+from .graph import EdgeEmbedder, count_per_bin, host_counts, masked_columns, radius_edges, radius_edges_transposed, static_edges
 from .irreps import get_irrep_seq, irreps_str, sh_irreps
 from .score_model import (AtomEncoder, GaussianSmearing, _Static, _edge_mlp, _i32, lig_feature_dims,
                           rec_atom_feature_dims, rec_residue_feature_dims)
@@ -166,7 +166,7 @@ class TensorProductScoreModel(_CGModel):
         st.NL, st.NR, st.NA = int(lig.pos.shape[0]), int(rec.pos.shape[0]), int(atom.pos.shape[0])
 
         def ptr_of(batch):
-            n = torch.bincount(batch, minlength=B)
+            n = count_per_bin(batch, B)
             p = torch.zeros(B + 1, dtype=torch.int32, device=dev)
             p[1:] = torch.cumsum(n, 0)
             return p, n
@@ -174,7 +174,11 @@ class TensorProductScoreModel(_CGModel):
         st.lig_ptr, nl = ptr_of(lig.batch)
         st.rec_ptr, nr = ptr_of(rec.batch)
         st.atom_ptr, na = ptr_of(atom.batch)
-        nl_h, nr_h, na_h = nl.tolist(), nr.tolist(), na.tolist()          # one host read per batch
+        hc = host_counts(data, ("ligand", "receptor", "atom"))            # from the collate's host tables: no device read
+        if hc is not None:
+            nl_h, nr_h, na_h = hc["ligand"], hc["receptor"], hc["atom"]
+        else:
+            nl_h, nr_h, na_h = nl.tolist(), nr.tolist(), na.tolist()      # one host read per batch
         st.nl_h = nl_h
         st.cap_cross = int(sum(a * b for a, b in zip(nl_h, nr_h)))
         st.cap_la = int(sum(a * b for a, b in zip(nl_h, na_h)))
@@ -186,12 +190,15 @@ class TensorProductScoreModel(_CGModel):
         if self.no_aminoacid_identities:
             rec_x = rec_x * 0
         mask = lig.edge_mask.bool()
-        st.tor_bonds = ll.edge_index[:, mask].long()
+        st.tor_bonds = masked_columns(ll.edge_index, mask, None if hc is None else sum(hc["n_tor"])).long()
         st.n_tor = int(st.tor_bonds.shape[1])
         if st.n_tor > 0:
             st.tor_batch = _i32(lig.batch[st.tor_bonds[0]])
-            nt = torch.bincount(lig.batch[st.tor_bonds[0]], minlength=B)
-            st.cap_tor = int(sum(t * min(a, 32) for t, a in zip(nt.tolist(), nl_h)))
+            if hc is not None:
+                nt_h = hc["n_tor"]
+            else:
+                nt_h = torch.bincount(lig.batch[st.tor_bonds[0]], minlength=B).tolist()
+            st.cap_tor = int(sum(t * min(a, 32) for t, a in zip(nt_h, nl_h)))
         st.lig_cat = self.lig_node_embedding.categorical(lig.x)
         from .graph import identity_edges
         st.center_edges = identity_edges(st.lig_ptr, st.NL)

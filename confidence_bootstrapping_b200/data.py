@@ -287,6 +287,12 @@ class Batch(HeteroData):
         b._g["_offs"] = offs
         # shape-level signature of everything but the ligand pose (sampling.reverse_diffusion: step-graph cache key)
         b._g["_static_sig"] = _static_signature(b) if device is not None else None
+        # host-side per-graph counts the models need for buffer caps (node counts are np.diff(_offs[type])): rotatable bonds
+        b._g["_n_tor_h"] = None
+        if "ligand" in first.node_types and "edge_mask" in first["ligand"].keys():
+            ms = [d["ligand"]._d["edge_mask"] for d in data_list]
+            if all(torch.is_tensor(m) and m.device.type == "cpu" for m in ms):
+                b._g["_n_tor_h"] = [int(m.bool().sum()) for m in ms]
         b._g["_ready"] = _ReadyEvent(None)
         if device is not None and torch.device(device).type == "cuda":
             ev = torch.cuda.Event()

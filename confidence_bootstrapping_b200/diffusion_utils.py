@@ -96,23 +96,48 @@ class LigandTopology:
     """Device-side tables of the shared ligand topology of a sampling batch (sampling.py:81,
     diffusion_utils.py:62-64): rotatable bonds (u, v) in edge order and the [R, N] rotation masks."""
 
-    def __init__(self, data, mask_rotate, device):
+    def __init__(self, data, mask_rotate, device, validate=True):
+        """`validate=False` skips the device-side orientation check (two host reads): sampling() runs the same check once on
+        the host graph instead (`check_rotation_masks`)."""
         B = int(data.num_graphs)
         lig, ll = data["ligand"], data["ligand", "ligand"]
         self.B = B
         self.N = int(lig.num_nodes) // B
         M = int(ll.num_edges) // B
         edge_index, edge_mask = ll.edge_index[:, :M], lig.edge_mask[:M].bool()
-        self.bond_uv = edge_index.t()[edge_mask].to(torch.int32).contiguous().to(device)
-        self.R = int(self.bond_uv.shape[0])
         mr = torch.as_tensor(np.asarray(mask_rotate)) if not torch.is_tensor(mask_rotate) else mask_rotate
+        n_tor_h = data._g.get("_n_tor_h") if isinstance(getattr(data, "_g", None), dict) and not data._g.get("_slices_stale") else None
+        if n_tor_h is not None and len(n_tor_h) == B:
+            # rotatable-bond count known on the host (collate): the masked selection needs no device read
+            idx = torch.nonzero_static(edge_mask, size=int(n_tor_h[0])).reshape(-1)
+            self.bond_uv = edge_index.index_select(1, idx).t().to(torch.int32).contiguous().to(device)
+        else:
+            self.bond_uv = edge_index.t()[edge_mask].to(torch.int32).contiguous().to(device)
+        self.R = int(self.bond_uv.shape[0])
         self.mask_rotate = mr.to(torch.uint8).contiguous().to(device)
         if self.R > 0:
             assert tuple(self.mask_rotate.shape) == (self.R, self.N), "mask_rotate does not match the topology"
-            u, v = self.bond_uv[:, 0].long(), self.bond_uv[:, 1].long()
-            idx = torch.arange(self.R, device=device)
-            # torsion.py:81-82: v must be on the rotating side, u on the fixed side
-            assert not bool(self.mask_rotate[idx, u].any()) and bool(self.mask_rotate[idx, v].all())
+            if validate:
+                u, v = self.bond_uv[:, 0].long(), self.bond_uv[:, 1].long()
+                idx = torch.arange(self.R, device=device)
+                # torsion.py:81-82: v must be on the rotating side, u on the fixed side
+                assert not bool(self.mask_rotate[idx, u].any()) and bool(self.mask_rotate[idx, v].all())
+
+
+def check_rotation_masks(graph, mask_rotate):
+    """The orientation check of LigandTopology on ONE host graph (torsion.py:81-82: for every rotatable bond (u, v) in edge
+    order, v is on the rotating side and u on the fixed side).  No-op for device-resident graphs."""
+    ei, em = graph["ligand", "ligand"].edge_index, graph["ligand"].edge_mask
+    if not (torch.is_tensor(ei) and ei.device.type == "cpu" and torch.is_tensor(em) and em.device.type == "cpu"):
+        return False
+    mr = np.asarray(mask_rotate.cpu() if torch.is_tensor(mask_rotate) else mask_rotate).astype(bool)
+    uv = ei.t()[em.bool()].numpy()
+    if uv.shape[0] == 0:
+        return True
+    assert mr.shape[0] == uv.shape[0], "mask_rotate does not match the topology"
+    r = np.arange(uv.shape[0])
+    assert not mr[r, uv[:, 0]].any() and mr[r, uv[:, 1]].all(), "mask_rotate orientation (torsion.py:81-82)"
+    return True
 
 
 def sde_step(pos, topo: LigandTopology, tr_score, rot_score, tor_score, coeffs, z_tr=None, z_rot=None, z_tor=None):

@@ -101,7 +101,7 @@ def static_edges(edge_index: torch.Tensor, n_agg: int):
     perm = torch.sort(agg, stable=True).indices
     row = agg[perm].to(torch.int32).contiguous()
     col = edge_index[1][perm].to(torch.int32).contiguous()
-    counts = torch.bincount(agg, minlength=n_agg)
+    counts = count_per_bin(agg, n_agg)       # (torch.bincount reads the maximum back to the host: a device sync)
     rowptr = torch.zeros(n_agg + 1, dtype=torch.int32, device=edge_index.device)
     rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
     e = int(edge_index.shape[1])
@@ -165,3 +165,38 @@ class EdgeEmbedder:
             _lib.edge_featurize(a)
         self._keep = (b1g,)  # stream-ordered allocator keeps this safe; reference held for clarity
         return out_attr, out_sh
+
+
+def host_counts(data, node_types):
+    """Per-graph node counts of `node_types` and rotatable-bond counts from the collate's HOST tables (data.Batch:
+    `_offs`, `_n_tor_h`) -- no device read, so building a batch's static tables does not wait for whatever is queued on the
+    stream.  None when the batch does not carry them or was edited in place (crop_beyond marks the tables stale)."""
+    g = getattr(data, "_g", None)
+    if not isinstance(g, dict) or g.get("_slices_stale") or g.get("_offs") is None or g.get("_n_tor_h") is None:
+        return None
+    offs = g["_offs"]
+    try:
+        counts = {nt: [int(v) for v in np.diff(np.asarray(offs[nt]))] for nt in node_types}
+    except KeyError:
+        return None
+    n = int(g.get("_num_graphs", 0))
+    if any(len(c) != n for c in counts.values()) or len(g["_n_tor_h"]) != n:
+        return None
+    counts["n_tor"] = [int(v) for v in g["_n_tor_h"]]
+    return counts
+
+
+def masked_columns(edge_index: torch.Tensor, mask: torch.Tensor, n_true=None) -> torch.Tensor:
+    """edge_index[:, mask]; with the number of set entries known on the host the selection runs without a device read."""
+    if n_true is None:
+        return edge_index[:, mask]
+    idx = torch.nonzero_static(mask, size=int(n_true)).reshape(-1)
+    return edge_index.index_select(1, idx)
+
+
+def count_per_bin(index: torch.Tensor, n_bins: int) -> torch.Tensor:
+    """torch.bincount(index, minlength=n_bins) for indices known to lie in [0, n_bins): no host read."""
+    out = torch.zeros(n_bins, dtype=torch.int64, device=index.device)
+    if index.numel():
+        out.index_add_(0, index.to(torch.int64), torch.ones(index.numel(), dtype=torch.int64, device=index.device))
+    return out

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .data import Batch, DataLoader
-from .diffusion_utils import LigandTopology, sde_step, set_time
+from .diffusion_utils import LigandTopology, check_rotation_masks, sde_step, set_time
 from .utils import crop_beyond
 
 
@@ -251,6 +251,17 @@ _conf_streams = {}
 PIPELINE_CONFIDENCE = os.environ.get("CB200_PIPELINE_CONFIDENCE", "1") != "0"
 
 
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _copy_streams:
+        _copy_streams[idx] = torch.cuda.Stream(device=idx)
+    return _copy_streams[idx]
+
+
 def _conf_stream(device):
     idx = torch.device(device).index
     idx = torch.cuda.current_device() if idx is None else idx
@@ -351,7 +362,7 @@ def _step_scalars(t_idx, inference_steps, tr_schedule, rot_schedule, tor_schedul
 def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device, t_to_sigma,
                       model_args, mask_rotate, noise_rows=None, no_random=False, ode=False, t_schedule=None,
                       no_final_step_noise=False, temp_sampling=(1.0, 1.0, 1.0), temp_psi=(0.0, 0.0, 0.0),
-                      temp_sigma_data=0.5, use_graph=None):
+                      temp_sigma_data=0.5, use_graph=None, validate_topology=True):
     """The hot loop of sampling.py:93-223 on a batch that already lives on the device: `inference_steps` x
     (score-model forward, K4 pose update).  Returns the final [B*N, 3] positions (also left in
     batch['ligand'].pos).  No host synchronisation inside.
@@ -422,7 +433,19 @@ def reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, 
     if reused is None and use_graph and _graph_cache:
         _graph_cache.clear()             # free the previous complex's graph pool before this batch allocates its own
     if reused is None:
-        topo = LigandTopology(batch, mask_rotate, device)
+        ready = batch._g.get("_ready") if hasattr(batch, "_g") else None
+        if getattr(ready, "ev", None) is not None and pos.is_cuda and not validate_topology:
+            # the topology tables are uploaded on the copy stream (a pageable H2D copy first synchronises ITS stream: on the
+            # main stream the host would wait for the previous batch's replays)
+            copy_s, main_s = _copy_stream(device), torch.cuda.current_stream(device)
+            copy_s.wait_event(ready.ev)
+            with torch.cuda.stream(copy_s):
+                topo = LigandTopology(batch, mask_rotate, device, validate=False)
+            main_s.wait_stream(copy_s)
+            for t in (topo.bond_uv, topo.mask_rotate):
+                t.record_stream(main_s)
+        else:
+            topo = LigandTopology(batch, mask_rotate, device, validate=validate_topology)
     warm_key = None
     if use_graph and isinstance(model, torch.nn.Module):
         from . import tensor_layers
@@ -650,13 +673,40 @@ def _sample_batches(leg, data_list, model, inference_steps, tr_schedule, rot_sch
         temp_psi = [temp_psi] * 3
     assert len(temp_sampling) == 3 and len(temp_psi) == 3
     n_legs = 0
-    for batch_id, batch in enumerate(loader):
+    # the orientation check of the rotation masks runs once on the host graph (the device-side one needs two host reads)
+    checked = check_rotation_masks(data_list[0], mask_rotate)
+    # Batches are collated on a COPY stream: pageable H2D copies are ordered behind whatever is queued on their stream, and on
+    # the main stream that is the previous batch's (or previous complex's) 20 graph replays -- the host would sit in
+    # cudaMemcpy for their whole duration instead of preparing this batch.  The main stream waits for the copy stream's event;
+    # every tensor of the batch is marked as used by the main stream for the allocator.
+    two_streams = leg.enabled and torch.device(device).type == "cuda"
+    it = iter(loader)
+    batch_id = -1
+    while True:
+        if two_streams:
+            copy_s, main_s = _copy_stream(device), torch.cuda.current_stream(device)
+            with torch.cuda.stream(copy_s):
+                batch = next(it, None)
+                if batch is not None:
+                    batch = batch.to(device)
+            if batch is not None:
+                main_s.wait_stream(copy_s)
+                for t in _tensor_refs(batch):
+                    if t.is_cuda:
+                        t.record_stream(main_s)
+        else:
+            batch = next(it, None)
+            if batch is not None:
+                batch = batch.to(device)
+        if batch is None:
+            break
+        batch_id += 1
         b = batch.num_graphs
-        batch = batch.to(device)
         pos = reverse_diffusion(batch, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, device,
                                 t_to_sigma, model_args, mask_rotate, noise_rows=min(batch_size, N), no_random=no_random,
                                 ode=ode, t_schedule=t_schedule, no_final_step_noise=no_final_step_noise,
-                                temp_sampling=temp_sampling, temp_psi=temp_psi, temp_sigma_data=temp_sigma_data)
+                                temp_sampling=temp_sampling, temp_psi=temp_psi, temp_sigma_data=temp_sigma_data,
+                                validate_topology=not checked)
         n = pos.shape[0] // b
         for i in range(b):
             data_list[batch_id * batch_size + i]["ligand"].pos = pos[i * n:n * (i + 1)]

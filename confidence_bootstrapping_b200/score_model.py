@@ -22,7 +22,8 @@ import torch
 from torch import nn
 
 from . import so3, torus
-from .graph import (EdgeEmbedder, EdgeList, identity_edges, radius_edges, radius_edges_transposed, static_edges)
+from .graph import (EdgeEmbedder, EdgeList, count_per_bin, host_counts, identity_edges, masked_columns, radius_edges, radius_edges_transposed,
+                    static_edges)
 from .irreps import full_tp_low_blocks, get_irrep_seq, irreps_str, sh_irreps
 from .synthetic import LIG_FEATURE_DIMS, REC_ATOM_FEATURE_DIMS, REC_RESIDUE_FEATURE_DIMS
 from .tensor_layers import Segment, TensorProductConvLayer
@@ -249,13 +250,17 @@ class TensorProductScoreModel(nn.Module):
         st.B, st.dev = B, dev
         st.lig_batch, st.rec_batch = _i32(lig.batch), _i32(rec.batch)
         st.NL, st.NR = int(lig.pos.shape[0]), int(rec.pos.shape[0])
-        nl = torch.bincount(lig.batch, minlength=B)
-        nr = torch.bincount(rec.batch, minlength=B)
+        nl = count_per_bin(lig.batch, B)
+        nr = count_per_bin(rec.batch, B)
         st.lig_ptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         st.lig_ptr[1:] = torch.cumsum(nl, 0)
         st.rec_ptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         st.rec_ptr[1:] = torch.cumsum(nr, 0)
-        nl_h, nr_h = nl.tolist(), nr.tolist()             # one host read per batch (sizes for buffer caps)
+        hc = host_counts(data, ("ligand", "receptor"))      # from the collate's host tables: no device read
+        if hc is not None:
+            nl_h, nr_h = hc["ligand"], hc["receptor"]
+        else:
+            nl_h, nr_h = nl.tolist(), nr.tolist()         # one host read per batch (sizes for buffer caps)
         st.nl_h, st.nr_h = nl_h, nr_h
         st.cap_cross = int(sum(a * b for a, b in zip(nl_h, nr_h)))
         st.cap_lig = int(sum(a * min(a - 1, 33) for a in nl_h if a > 0)) + 1
@@ -269,12 +274,15 @@ class TensorProductScoreModel(nn.Module):
             st.rec_x = st.rec_x * 0
         # rotatable bonds (score_model.py:650-652)
         mask = lig.edge_mask.bool()
-        st.tor_bonds = ll.edge_index[:, mask].long()
-        st.n_tor = int(st.tor_bonds.shape[1])              # host read, once per batch
+        st.tor_bonds = masked_columns(ll.edge_index, mask, None if hc is None else sum(hc["n_tor"])).long()
+        st.n_tor = int(st.tor_bonds.shape[1])              # (a host read, once per batch, without the host tables)
         if st.n_tor > 0:
             st.tor_batch = _i32(lig.batch[st.tor_bonds[0]])
-            nt = torch.bincount(lig.batch[st.tor_bonds[0]], minlength=B)
-            st.cap_tor = int(sum(t * min(a, 32) for t, a in zip(nt.tolist(), nl_h)))
+            if hc is not None:
+                nt_h = hc["n_tor"]
+            else:
+                nt_h = torch.bincount(lig.batch[st.tor_bonds[0]], minlength=B).tolist()
+            st.cap_tor = int(sum(t * min(a, 32) for t, a in zip(nt_h, nl_h)))
         st.lig_cat = self.lig_node_embedding.categorical(lig.x)           # pose/time independent part
         st.center_edges = identity_edges(st.lig_ptr, st.NL)
         st.inv_nl = (1.0 / nl.float().clamp(min=1)).unsqueeze(1)
