@@ -453,3 +453,38 @@ def test_filtering_leg_runs_one_batch_behind_and_keeps_the_order():
     out = leg.finish()
     assert calls == [0, 1, 2] and [float(o[0]) for o in out] == [1.0, 2.0, 3.0]
     assert leg.finish() == []
+
+
+def test_host_count_tables_replace_the_device_reads():
+    """The per-batch set-up of the models takes node / rotatable-bond counts from the collate's host tables (graph.host_counts),
+    selects masked columns with the host-known count and counts per bin without torch.bincount: same values, no device read."""
+    import copy
+    from confidence_bootstrapping_b200.diffusion_utils import check_rotation_masks
+    from confidence_bootstrapping_b200.graph import count_per_bin, host_counts, masked_columns
+    from confidence_bootstrapping_b200.sampling import _mask_rotate_of
+    graphs = [make_complex(70 + i, 20 + 7 * i, 8 + 2 * i, all_atoms=True) for i in range(3)]
+    b = Batch.from_data_list(copy.deepcopy(graphs), device="cpu")
+    hc = host_counts(b, ("ligand", "receptor", "atom"))
+    for nt in ("ligand", "receptor", "atom"):
+        assert hc[nt] == torch.bincount(b[nt].batch, minlength=3).tolist()
+    mask = b["ligand"].edge_mask.bool()
+    lig_edge_graph = b["ligand"].batch[b["ligand", "ligand"].edge_index[0]]
+    assert hc["n_tor"] == torch.bincount(lig_edge_graph[mask], minlength=3).tolist()
+    ei = b["ligand", "ligand"].edge_index
+    assert torch.equal(masked_columns(ei, mask, sum(hc["n_tor"])), ei[:, mask]) and torch.equal(masked_columns(ei, mask), ei[:, mask])
+    idx = torch.tensor([4, 0, 4, 2])
+    assert torch.equal(count_per_bin(idx, 6), torch.bincount(idx, minlength=6))
+    assert count_per_bin(idx[:0], 3).tolist() == [0, 0, 0]
+    # tables are refused once the batch was edited in place; a host collate carries them too
+    b._g["_slices_stale"] = True
+    assert host_counts(b, ("ligand",)) is None
+    assert host_counts(Batch.from_data_list(copy.deepcopy(graphs)), ("ligand",)) == {"ligand": hc["ligand"], "n_tor": hc["n_tor"]}
+    # the host-side orientation check of the rotation masks (torsion.py:81-82)
+    g0 = graphs[0]
+    mr = _mask_rotate_of(g0)
+    assert check_rotation_masks(g0, mr)
+    bad = np.asarray(mr).copy()
+    if bad.shape[0] > 0:
+        bad[0] = ~bad[0]
+        with pytest.raises(AssertionError):
+            check_rotation_masks(g0, bad)
