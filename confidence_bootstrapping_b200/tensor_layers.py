@@ -40,12 +40,21 @@ def _workspace(n_floats, dev):
     caching allocator (the confidence leg's shapes change with every crop_beyond: single 250-380 ms steps among 165 ms ones)
     disappears.  While a CUDA graph is being captured the buffer comes from the graph's memory pool instead, so that the
     graph owns what it points to."""
-    if DEBUG_KEEP_WORKSPACE is not None or torch.cuda.is_current_stream_capturing():
+    if DEBUG_KEEP_WORKSPACE is not None:
         return torch.empty(n_floats, dtype=torch.float32, device=dev)
+    if torch.cuda.is_current_stream_capturing():
+        # graph pool: 25 % head-room in 256 MB steps, so that the block freed by the previous complex's graph fits the next
+        # complex's slightly different request instead of forcing a new multi-GB cudaMalloc (which stalls the device)
+        step = 64 << 20
+        n_alloc = min(-(-int(n_floats * 1.25) // step) * step, max(WORKSPACE_BYTES // 4, n_floats))
+        return torch.empty(max(n_alloc, n_floats), dtype=torch.float32, device=dev)[:n_floats]
     key = (torch.device(dev).index, torch.cuda.current_stream(dev).cuda_stream)
     buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < n_floats:
-        grow = n_floats if buf is None else max(n_floats, min(int(buf.numel() * 1.5), WORKSPACE_BYTES // 4))
+        # 2x head-room (within the cap): the filtering leg's request follows the cropped system size, which varies 2x between
+        # batches, and a multi-GB cudaMalloc in the middle of a run stalls the device (single 250-380 ms steps)
+        cap = max(WORKSPACE_BYTES // 4, n_floats)
+        grow = min(2 * n_floats, cap) if buf is None else min(max(n_floats, 2 * buf.numel()), cap)
         _WORKSPACES[key] = buf = None          # release the old block to the allocator before asking for the larger one
         _WORKSPACES[key] = buf = torch.empty(grow, dtype=torch.float32, device=dev)
     return buf[:n_floats]
