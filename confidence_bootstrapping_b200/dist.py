@@ -116,16 +116,31 @@ def gather_results(local_ids: Sequence[int], poses: Sequence[torch.Tensor], conf
     return out_p, out_c
 
 
-def sample_complexes(complexes: Sequence, n_samples: int, sample_fn, costs: Optional[Sequence[float]] = None, device=None):
+def sample_complexes(complexes: Sequence, n_samples: int, sample_fn=None, costs: Optional[Sequence[float]] = None, device=None,
+                     sample_many_fn=None):
     """Shard `complexes` over the ranks, run `sample_fn(complex, n_samples) -> (poses [S,N,3], conf [S] or None)`
-    on the local shard, and all-gather.  Returns (poses_per_complex, conf_per_complex) on every rank."""
+    on the local shard, and all-gather.  Returns (poses_per_complex, conf_per_complex) on every rank.
+
+    `sample_many_fn(list_of_complexes, n_samples) -> [(poses, conf), ...]` (one entry per complex, in order) replaces the
+    per-complex calls by ONE call for the rank's shard -- the hook for `sampling.sampling_many`, which overlaps the filtering leg
+    of a complex with the collate / capture / steps of the next one."""
+    if (sample_fn is None) == (sample_many_fn is None):
+        raise ValueError("sample_complexes: pass exactly one of sample_fn / sample_many_fn")
     rank, world = _world()
     if costs is None:
         costs = [estimate_cost(int(c["ligand"].num_nodes), int(c["receptor"].num_nodes), n_samples) for c in complexes]
     mine = partition_lpt(costs, world)[rank]
     poses, confs = [], []
-    for i in mine:
-        p, c = sample_fn(complexes[i], n_samples)
-        poses.append(p)
-        confs.append(c)
+    if sample_many_fn is not None:
+        res = list(sample_many_fn([complexes[i] for i in mine], n_samples)) if mine else []
+        if len(res) != len(mine):
+            raise RuntimeError(f"sample_many_fn returned {len(res)} results for {len(mine)} complexes")
+        for p, c in res:
+            poses.append(p)
+            confs.append(c)
+    else:
+        for i in mine:
+            p, c = sample_fn(complexes[i], n_samples)
+            poses.append(p)
+            confs.append(c)
     return gather_results(mine, poses, confs, len(complexes), device=device)

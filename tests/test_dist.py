@@ -56,7 +56,11 @@ def _worker(rank, world, port, n_complexes, q):
 
         # device=None: a rank that owns no complex (n_complexes=1) must still pick a device the backend accepts
         poses, confs = cbdist.sample_complexes(complexes, 4, sample_fn, device=None)
-        ok = True
+        # the same through the one-call-per-shard hook (what sampling.sampling_many plugs into)
+        poses2, confs2 = cbdist.sample_complexes(complexes, 4, device=None,
+                                                 sample_many_fn=lambda cs, n: [_fake_result((c["ligand"].num_nodes - 5) // 3, n) for c in cs])
+        ok = all(torch.equal(a, b) for a, b in zip(poses, poses2))
+        ok &= all((a is None and b is None) or torch.equal(a, b) for a, b in zip(confs, confs2))
         for i in range(n_complexes):
             p, c = _fake_result(i, 4)
             ok &= torch.equal(poses[i], p)
